@@ -1,0 +1,296 @@
+// FlashAttention-style softmax(Q K^T * scale) V for sm_100a on tcgen05 + TMEM + TMA.
+//
+// Replaces every CrossAttention.forward / AttnBlock.forward variant of the reference
+// (modules/sd_hijack_optimizations.py:180-655: split, Doggettx, InvokeAI, sub-quadratic, xformers, sdp):
+// one kernel for UNet self-attention (Nk = Nq in {4096,1024,256,64}), cross-attention (Nk = 77*k) and the
+// VAE AttnBlock (single head, d = 512, run as two passes over 256-wide halves of V).
+//
+// Inputs are per-head padded tensors [B*H, tokens, dpad] (dpad multiple of 64, pad columns zero) written by
+// the q/k/v projection GEMM's EPI_HEADS epilogue; output is merged-head [B*Nq, H*d] for the out-projection.
+//
+// CTA = one 128-row query tile of one (batch, head):
+//   warp 0    : TMA producer. Q slabs once (or streamed when d = 512), then K_i / V_i slabs (128 x 64 elements,
+//               16 KB, 128B swizzle) through one in-order ring, in exactly the order the MMA warp consumes them.
+//   warp 1    : tcgen05.mma issuer.  S_i = Q K_i^T -> TMEM (double buffered);  O += P_i V_i -> TMEM.
+//               V is used as an MN-major B operand straight from its natural [kv, dv] layout.
+//   warps 2-5 : online softmax, one thread per query row (tcgen05.ld 32x32b): running max / sum in fp32,
+//               P written to shared memory in the UMMA K-major 128B-swizzle layout, O rescaled in TMEM only
+//               when a row max moved; final 1/l scaling and store.
+#include "attention.cuh"
+#include <algorithm>
+
+namespace sdxe {
+
+static constexpr int SLAB_BYTES = 16384;  // 128 rows x 64 x 2 B
+static constexpr int ATT_THREADS = 192;
+static constexpr int TM_S0 = 0, TM_O = 256;  // TMEM columns: S buffers at 0 / 128, O at 256..511
+
+template <bool BF16>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs a) {
+  using T = T16<BF16>;
+  using TT = typename T::type;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sbase = raw + pad;
+
+  const int NS = a.num_slots;
+  const int q_slabs = a.q_resident ? a.dqk_slabs : 0;
+  const uint32_t sQ = sbase;
+  const uint32_t sRing = sQ + q_slabs * SLAB_BYTES;
+  const uint32_t sP = sRing + NS * SLAB_BYTES;
+  const uint32_t bar_base = sP + 2 * SLAB_BYTES;
+  auto slot_full = [&](int s) { return bar_base + 8u * s; };
+  auto slot_empty = [&](int s) { return bar_base + 8u * (NS + s); };
+  const uint32_t q_full = bar_base + 8u * (2 * NS);
+  auto s_full = [&](int i) { return bar_base + 8u * (2 * NS + 1 + i); };
+  const uint32_t p_ready = bar_base + 8u * (2 * NS + 3);
+  const uint32_t pv_done = bar_base + 8u * (2 * NS + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int bh = blockIdx.y;
+  const int nblk = (a.Nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
+    mbar_init(q_full, 1);
+    mbar_init(s_full(0), 1);
+    mbar_init(s_full(1), 1);
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&a.tmQ);
+    tma_prefetch_desc(&a.tmK);
+    tma_prefetch_desc(&a.tmV);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      if (a.q_resident) {
+        mbar_expect_tx(q_full, a.dqk_slabs * SLAB_BYTES);
+        for (int c = 0; c < a.dqk_slabs; ++c) tma_load_3d(sQ + c * SLAB_BYTES, &a.tmQ, q_full, c * 64, q0, bh);
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      auto push = [&](const CUtensorMap* tm, int c0, int r0) {
+        mbar_wait(slot_empty(slot), phase ^ 1u);
+        mbar_expect_tx(slot_full(slot), SLAB_BYTES);
+        tma_load_3d(sRing + slot * SLAB_BYTES, tm, slot_full(slot), c0, r0, bh);
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+      };
+      for (int i = 0; i <= nblk; ++i) {
+        if (i < nblk) {
+          for (int c = 0; c < a.dqk_slabs; ++c) {
+            if (!a.q_resident) push(&a.tmQ, c * 64, q0);
+            push(&a.tmK, c * 64, i * 128);
+          }
+        }
+        if (i >= 1)
+          for (int vs = 0; vs < a.dv_slabs; ++vs) push(&a.tmV, vs * 64, (i - 1) * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, 128, 128, 0, 0);
+      const uint32_t idesc_pv = umma_idesc(BF16 ? 1 : 0, 128, 64, 0, 1);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto pop = [&]() -> uint32_t {  // wait for the next slab in ring order, return its smem address
+        mbar_wait(slot_full(slot), phase);
+        return sRing + slot * SLAB_BYTES;
+      };
+      auto release = [&]() {  // slab is freed when the MMAs issued so far complete
+        tc_commit(slot_empty(slot));
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+      };
+      if (a.q_resident) mbar_wait(q_full, 0);
+      for (int i = 0; i <= nblk; ++i) {
+        if (i < nblk) {
+          const uint32_t d_s = tmem_base + TM_S0 + (uint32_t)((i & 1) * 128);
+          for (int c = 0; c < a.dqk_slabs; ++c) {
+            uint32_t q_addr;
+            int q_slot_held = 0;
+            if (a.q_resident) q_addr = sQ + c * SLAB_BYTES;
+            else { q_addr = pop(); q_slot_held = 1; }
+            // when Q is streamed its slab must stay valid until the K slab's MMAs are issued:
+            // advance manually past it, release both afterwards (commit order == ring order).
+            int q_slot = slot;
+            uint32_t q_phase = phase;
+            if (q_slot_held) { if (++slot == NS) { slot = 0; phase ^= 1u; } }
+            const uint32_t k_addr = pop();
+            tc_fence_after();
+            const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
+            const uint64_t kd = umma_desc_sw128(k_addr, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+            if (q_slot_held) { tc_commit(slot_empty(q_slot)); (void)q_phase; }
+            release();
+          }
+          tc_commit(s_full(i & 1));
+        }
+        if (i >= 1) {
+          const int j = i - 1;  // O += P_j V_j
+          mbar_wait(p_ready, (uint32_t)(j & 1));
+          tc_fence_after();
+          for (int vs = 0; vs < a.dv_slabs; ++vs) {
+            const uint32_t v_addr = pop();
+            tc_fence_after();
+            const uint32_t d_o = tmem_base + TM_O + (uint32_t)(vs * 64);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t pd = umma_desc_sw128(sP + (k >> 2) * SLAB_BYTES, 16, 1024) + 2 * (k & 3);
+              const uint64_t vd = umma_desc_sw128(v_addr + k * 2048, SLAB_BYTES, 1024);
+              tc_mma_f16(d_o, pd, vd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+            release();
+          }
+          tc_commit(pv_done);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = a.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int i = 0; i < nblk; ++i) {
+      mbar_wait(s_full(i & 1), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + TM_S0 + (uint32_t)((i & 1) * 128) + lane_base;
+      const int kv0 = i * 128;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = (kv0 + c * 32 + j < a.Nk) ? __uint_as_float(r[j]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * sl2);  // first block: exp2(-inf) = 0
+      const float mb = m_new * sl2;
+      if (i >= 1) {
+        mbar_wait(pv_done, (uint32_t)((i - 1) & 1));  // P buffer free, O holds blocks < i
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          for (int c = 0; c < a.dv_slabs * 2; ++c) {
+            uint32_t r[32];
+            const uint32_t t_o = tmem_base + TM_O + lane_base + c * 32;
+            tmem_ld32(t_o, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+            tmem_st32(t_o, r);
+          }
+          tc_wait_st();
+        }
+      }
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float v0 = (kv0 + c * 32 + j < a.Nk) ? __uint_as_float(r[j]) : -INFINITY;
+          const float v1 = (kv0 + c * 32 + j + 1 < a.Nk) ? __uint_as_float(r[j + 1]) : -INFINITY;
+          const float p0 = exp2f(fmaf(v0, sl2, -mb));
+          const float p1 = exp2f(fmaf(v1, sl2, -mb));
+          sum += p0 + p1;
+          pk[j >> 1] = T::pack(p0, p1);
+        }
+        // P tile: two K-major 128B-swizzle atoms of 64 kv columns; this chunk = 4 x 16 B of row `row`
+        const uint32_t p_row = sP + (c >> 1) * SLAB_BYTES + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[q * 4 + 0]),
+                       "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
+                       : "memory");
+        }
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> out[b, q, h*dv + j]
+    mbar_wait(pv_done, (uint32_t)((nblk - 1) & 1));
+    tc_fence_after();
+    const int q = q0 + row;
+    const float inv_l = 1.f / l_run;
+    const int b = bh / a.H, h = bh - b * a.H;
+    TT* orow = reinterpret_cast<TT*>(a.out) + ((size_t)b * a.Nq + q) * a.ldo + a.out_col0 + h * a.dv;
+    for (int c = 0; c * 32 < a.dv; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + TM_O + lane_base + c * 32, r);
+      tc_wait_ld();
+      if (q < a.Nq) {
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+          if (c * 32 + g + 8 <= a.dv) {
+            uint4 u;
+            u.x = T::pack(__uint_as_float(r[g + 0]) * inv_l, __uint_as_float(r[g + 1]) * inv_l);
+            u.y = T::pack(__uint_as_float(r[g + 2]) * inv_l, __uint_as_float(r[g + 3]) * inv_l);
+            u.z = T::pack(__uint_as_float(r[g + 4]) * inv_l, __uint_as_float(r[g + 5]) * inv_l);
+            u.w = T::pack(__uint_as_float(r[g + 6]) * inv_l, __uint_as_float(r[g + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
+  AttnArgs a = a_in;
+  if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {
+    set_last_error(__FILE__, __LINE__, "attention: unsupported head size");
+    return -1;
+  }
+  a.q_resident = a.dqk_slabs <= 3 ? 1 : 0;
+  const int q_slabs = a.q_resident ? a.dqk_slabs : 0;
+  const int budget = (224 * 1024 - 2048) / SLAB_BYTES;  // slabs that fit beside barriers + alignment slack
+  a.num_slots = std::min(10, budget - 2 - q_slabs);
+  if (a.num_slots < 2) { set_last_error(__FILE__, __LINE__, "attention: smem"); return -1; }
+  const size_t smem = (size_t)(q_slabs + a.num_slots + 2) * SLAB_BYTES + 8 * (2 * a.num_slots + 5) + 16 + 1024;
+  auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[bf16 ? 1 : 0]) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[bf16 ? 1 : 0] = true;
+  }
+  dim3 grid((a.Nq + 127) / 128, a.B * a.H);
+  kern<<<grid, ATT_THREADS, smem, stream>>>(a);
+  SDXE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdxe

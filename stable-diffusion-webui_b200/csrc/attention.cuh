@@ -1,0 +1,25 @@
+// Argument block of the tcgen05 flash-attention kernel (attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sdxe {
+
+struct alignas(64) AttnArgs {
+  CUtensorMap tmQ;  // 3D {dqk_pad, Nq, B*H}, box 64 x 128 x 1
+  CUtensorMap tmK;  // 3D {dqk_pad, Nk, B*H}
+  CUtensorMap tmV;  // 3D {dv_pad,  Nk, B*H}
+  int B, H, Nq, Nk;
+  int dqk_slabs;    // dqk_pad / 64  (1..8)
+  int dv_slabs;     // dv_pad / 64   (1..4)
+  int dv;           // valid value columns per head that are stored (multiple of 8)
+  int q_resident;   // set by the launcher
+  int num_slots;    // set by the launcher
+  float scale_log2; // softmax scale * log2(e)
+  void* out;        // [B*Nq, ldo] 16-bit; head h writes columns out_col0 + h*dv ...
+  int ldo;
+  int out_col0;
+};
+
+int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
+
+}  // namespace sdxe

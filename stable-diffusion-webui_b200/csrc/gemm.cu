@@ -1,0 +1,323 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M, N] = A[M, K] * W[N, K]^T  (+ bias + per-sample vector + residual | GEGLU | head scatter)
+//
+// Replaces, on the UNet / VAE hot path of the reference (all PyTorch library dispatch there):
+//   * ResBlock / Upsample / VAE conv3x3      (ldm openaimodel.py ResBlock) -> conv mode
+//   * conv1x1 proj_in/proj_out/skip, Linear q/k/v/out/FF                          -> plain mode
+//   * GEGLU (ldm attention.py GEGLU: x * gelu(gate))                                         -> EPI_GEGLU
+//   * the q/k/v head split of sd_hijack_optimizations.py:525-527                              -> EPI_HEADS
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x BN):
+//   warp 0   : TMA producer. A tile = 128 rows x 64 K (16 KB, 128B swizzle). In conv mode the A tile is a
+//              4D NHWC box (64 ch x W x bh x bn) fetched at the tap's (dx-1, dy-1) offset: TMA's out-of-bounds
+//              zero fill IS the convolution padding, so no im2col buffer ever exists.
+//   warp 1   : tcgen05.mma issuer (single thread), fp32 accumulators in TMEM, double buffered (2 x BN columns)
+//   warps 2-5: epilogue. tcgen05.ld the accumulator (thread = row), fuse bias / timestep-embedding vector /
+//              residual / GEGLU, convert to 16 bit, store.
+#include "gemm.cuh"
+#include <algorithm>
+#include <cstdio>
+
+namespace sdxe {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int TMEM_COLS = 512;
+
+template <bool BF16>
+struct Epi {
+  using T = T16<BF16>;
+
+  // 8 consecutive output columns of one row -> one 16-byte store
+  static SDXE_DEVINL void store8(void* dst, const float* v) {
+    uint4 u;
+    u.x = T::pack(v[0], v[1]);
+    u.y = T::pack(v[2], v[3]);
+    u.z = T::pack(v[4], v[5]);
+    u.w = T::pack(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+  static SDXE_DEVINL void add_bias8(float* v, const float* __restrict__ b, int n, int N) {
+    if (n + 8 <= N) {
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(b + n));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(b + n + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < N) v[j] += __ldg(b + n + j);
+    }
+  }
+  static SDXE_DEVINL void add_res8(float* v, const void* res) {
+    uint4 u = *reinterpret_cast<const uint4*>(res);
+    float2 f;
+    f = T::unpack(u.x); v[0] += f.x; v[1] += f.y;
+    f = T::unpack(u.y); v[2] += f.x; v[3] += f.y;
+    f = T::unpack(u.z); v[4] += f.x; v[5] += f.y;
+    f = T::unpack(u.w); v[6] += f.x; v[7] += f.y;
+  }
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
+  using E = Epi<BF16>;
+  using TT = typename T16<BF16>::type;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw + pad;
+
+  const int S = a.num_stages;
+  const int BN = a.BN;
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)BN * 128u;
+  const uint32_t bar_base = smem_base + S * stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (a.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&a.tmA);
+    tma_prefetch_desc(&a.tmB);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int m0 = m_blk * BLOCK_M;
+        int img0 = 0, h0 = 0;
+        if (a.conv) {
+          const int hw = a.H * a.W;
+          img0 = m0 / hw;
+          h0 = (m0 % hw) / a.W;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, stage_bytes);
+          if (a.conv) {
+            const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, dx - 1, h0 + dy - 1, img0);
+          } else {
+            const int k0 = kb * BLOCK_K;
+            if (k0 < a.K1) tma_load_2d(sA, &a.tmA, fb, k0, m0);
+            else tma_load_2d(sA, &a.tmA2, fb, k0 - a.K1, m0);
+          }
+          tma_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BF16 ? 1 : 0, BLOCK_M, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sB, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
+            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int Nst = (a.epi == EPI_GEGLU) ? (a.N / 2) : ((a.N + 7) & ~7);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int m = m_blk * BLOCK_M + row;
+      const bool row_ok = m < a.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+      const float* rv = nullptr;
+      if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.N;
+
+      if (a.epi == EPI_GEGLU) {
+        const int half = BN >> 1;
+        for (int c0 = 0; c0 < half; c0 += 32) {
+          const int nc = min(32, half - c0);
+          uint32_t rv_[32], rg_[32];
+          if (nc == 32) {
+            tmem_ld32(t_row + c0, rv_);
+            tmem_ld32(t_row + half + c0, rg_);
+          } else {
+            tmem_ld16(t_row + c0, rv_);
+            tmem_ld16(t_row + half + c0, rg_);
+          }
+          tc_wait_ld();
+          if (row_ok) {
+            for (int g = 0; g < nc; g += 8) {
+              const int nb = n_blk * BN + c0 + g;        // column in the interleaved weight/bias order
+              const int no = n_blk * half + c0 + g;      // output column
+              float v[8], gt[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] = __uint_as_float(rv_[g + j]);
+                gt[j] = __uint_as_float(rg_[g + j]);
+              }
+              if (a.bias) {
+                E::add_bias8(v, a.bias, nb, a.N);
+                E::add_bias8(gt, a.bias, nb + half, a.N);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] * gelu_erf_f(gt[j]);
+              if (no + 8 <= Nst) E::store8(reinterpret_cast<TT*>(a.out) + (size_t)m * a.ldo + no, v);
+            }
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int nc = min(32, BN - c0);
+          uint32_t r[32];
+          if (nc == 32) tmem_ld32(t_row + c0, r);
+          else tmem_ld16(t_row + c0, r);
+          tc_wait_ld();
+          if (row_ok) {
+            for (int g = 0; g < nc; g += 8) {
+              const int n = n_blk * BN + c0 + g;
+              if (n >= Nst) break;
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
+              if (a.bias) E::add_bias8(v, a.bias, n, a.N);
+              if (rv) E::add_bias8(v, rv, n, a.N);
+              if (a.epi == EPI_PLAIN) {
+                if (a.residual)
+                  E::add_res8(v, reinterpret_cast<const TT*>(a.residual) + (size_t)m * a.ldr + n);
+                E::store8(reinterpret_cast<TT*>(a.out) + (size_t)m * a.ldo + n, v);
+              } else {  // EPI_HEADS: column n -> (which tensor, head, offset); row m -> (batch, token)
+                const int C = a.heads * a.head_dim;
+                const int which = n / C, cc = n - which * C;
+                const int head = cc / a.head_dim, off = cc - head * a.head_dim;
+                const int b = m / a.tokens, tok = m - b * a.tokens;
+                TT* dst = reinterpret_cast<TT*>(a.outs[which]) +
+                          ((size_t)(b * a.heads + head) * a.tokens + tok) * a.head_pad + off;
+                E::store8(dst, v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int gemm_pick_stages(int BN) {
+  const int stage_bytes = A_STAGE_BYTES + BN * 128;
+  int s = (200 * 1024) / stage_bytes;
+  return std::max(2, std::min(s, 8));
+}
+
+int gemm_pick_bn(int M, int N, int K, int epi) {
+  (void)K;
+  const int sms = num_sms();
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  double best = 1e30;
+  int best_bn = 16;
+  for (int bn = 16; bn <= 256; bn += 16) {
+    if (epi == EPI_GEGLU && (bn % 32 != 0 || N % bn != 0)) continue;
+    const int num_n = (N + bn - 1) / bn;
+    const long tiles = (long)num_m * num_n;
+    const long waves = (tiles + sms - 1) / sms;
+    // cycles per 64-deep k-block: tensor pipe (2*BN) vs. operand fetch through L2 (~48 B/clk/SM) + fixed overhead
+    const double kb = std::max(2.0 * bn, (A_STAGE_BYTES + 128.0 * bn) / 48.0) + 24.0;
+    const double cost = waves * kb;
+    if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
+  if (a.BN % 16 != 0 || a.BN < 16 || a.BN > 256) { set_last_error(__FILE__, __LINE__, "gemm: bad BN"); return -1; }
+  if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
+  if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
+  const int stage_bytes = A_STAGE_BYTES + a.BN * 128;
+  const size_t smem = (size_t)a.num_stages * stage_bytes + 8 * (2 * a.num_stages + 4) + 16 + 1024;
+  const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
+  const int tiles = num_m * num_n;
+  if (tiles <= 0) return 0;
+  const int grid = std::min(tiles, num_sms());
+  static bool attr_done[2] = {false, false};
+  auto kern = bf16 ? gemm_kernel<true> : gemm_kernel<false>;
+  if (!attr_done[bf16 ? 1 : 0]) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[bf16 ? 1 : 0] = true;
+  }
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
+  SDXE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdxe

@@ -1,0 +1,610 @@
+// Bandwidth-bound kernels: GroupNorm / LayerNorm, layout gathers, embeddings, weight repack, sampler-step fusions.
+// All activation tensors are 16-bit NHWC ([n, h*w, c]); vectors of 8 channels (16 B) per thread access.
+#include "kernels.cuh"
+#include <algorithm>
+#include <atomic>
+
+namespace sdxe {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+#define SDXE_LAUNCH_CHECK()                 \
+  do {                                      \
+    count_launch();                         \
+    SDXE_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
+
+SDXE_DEVINL float load_any(const void* p, int dtype, int64_t i) {
+  if (dtype == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  if (dtype == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return reinterpret_cast<const float*>(p)[i];
+}
+SDXE_DEVINL void store_any(void* p, int dtype, int64_t i, float v) {
+  if (dtype == DT_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else if (dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+template <bool BF16>
+SDXE_DEVINL void unpack8(const uint4& u, float* v) {
+  float2 f;
+  f = T16<BF16>::unpack(u.x); v[0] = f.x; v[1] = f.y;
+  f = T16<BF16>::unpack(u.y); v[2] = f.x; v[3] = f.y;
+  f = T16<BF16>::unpack(u.z); v[4] = f.x; v[5] = f.y;
+  f = T16<BF16>::unpack(u.w); v[6] = f.x; v[7] = f.y;
+}
+template <bool BF16>
+SDXE_DEVINL uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = T16<BF16>::pack(v[0], v[1]);
+  u.y = T16<BF16>::pack(v[2], v[3]);
+  u.z = T16<BF16>::pack(v[4], v[5]);
+  u.w = T16<BF16>::pack(v[6], v[7]);
+  return u;
+}
+template <bool BF16>
+SDXE_DEVINL float round16(float v) { return T16<BF16>::to_f(T16<BF16>::from_f(v)); }
+
+// =============================================================================================================
+// GroupNorm (ldm GroupNorm32: statistics in fp32 — modules/devices.py:284-295 states the upcast)
+// =============================================================================================================
+template <bool BF16>
+__global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
+                                float* __restrict__ stats, int hw, int groups, int pix_per_block) {
+  extern __shared__ float gs[];  // [2 * groups]
+  const int C = c1 + c2, V = C >> 3, cpg = C / groups;
+  const int n = blockIdx.y;
+  const int vec = threadIdx.x % V, prow = threadIdx.x / V, rpi = blockDim.x / V;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) gs[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  const int c = vec * 8;
+  if (prow < rpi) {
+    for (int p = p0 + prow; p < p1; p += rpi) {
+      const size_t pix = (size_t)n * hw + p;
+      const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
+      float v[8];
+      unpack8<BF16>(u, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      atomicAdd(&gs[2 * g], s[j]);
+      atomicAdd(&gs[2 * g + 1], ss[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * groups + i], gs[i]);
+}
+
+template <bool BF16, bool SILU>
+__global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
+                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, uint4* __restrict__ out, int n_img, int hw, int groups,
+                                float eps) {
+  const int C = c1 + c2, V = C >> 3, cpg = C / groups;
+  const float inv_cnt = 1.f / ((float)hw * (float)cpg);
+  const size_t total = (size_t)n_img * hw * V;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int vec = (int)(idx % V);
+    const size_t pix = idx / V;
+    const int n = (int)(pix / hw);
+    const int c = vec * 8;
+    const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
+    float v[8];
+    unpack8<BF16>(u, v);
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      if (g != g_prev) {
+        const float sm = stats[((size_t)n * groups + g) * 2], sq = stats[((size_t)n * groups + g) * 2 + 1];
+        mean = sm * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        rstd = rsqrtf(var + eps);
+        g_prev = g;
+      }
+      float y = (v[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      if (SILU) y = silu_f(y);
+      v[j] = y;
+    }
+    out[idx] = pack8<BF16>(v);
+  }
+}
+
+int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* out,
+                      float* stats, int n, int hw, int groups, float eps, bool silu, bool bf16, cudaStream_t s) {
+  if (x2 == nullptr) c2 = 0;
+  const int C = c1 + c2;
+  if (C % 8 || c1 % 8 || C % groups) { set_last_error(__FILE__, __LINE__, "group_norm: channel alignment"); return -1; }
+  const int V = C / 8;
+  if (V > 1024) { set_last_error(__FILE__, __LINE__, "group_norm: too many channels"); return -1; }
+  SDXE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, s));
+  const int rpi = std::max(1, 256 / V);
+  const int threads = V * rpi;
+  int chunks = std::max(1, std::min((num_sms() * 4 + n - 1) / n, (hw + rpi * 4 - 1) / (rpi * 4)));
+  const int ppb = (hw + chunks - 1) / chunks;
+  chunks = (hw + ppb - 1) / ppb;
+  dim3 grid(chunks, n);
+  const size_t sm = sizeof(float) * 2 * groups;
+  if (bf16)
+    gn_stats_kernel<true><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, hw, groups, ppb);
+  else
+    gn_stats_kernel<false><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, hw, groups, ppb);
+  SDXE_LAUNCH_CHECK();
+  const size_t total = (size_t)n * hw * V;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+#define GN_APPLY(B, S)                                                                                              \
+  gn_apply_kernel<B, S><<<blocks, 256, 0, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, gamma, beta, \
+                                               (uint4*)out, n, hw, groups, eps)
+  if (bf16) { if (silu) GN_APPLY(true, true); else GN_APPLY(true, false); }
+  else { if (silu) GN_APPLY(false, true); else GN_APPLY(false, false); }
+#undef GN_APPLY
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
+// LayerNorm (fp32 statistics, as torch autocast runs layer_norm in fp32) — one warp per row
+// =============================================================================================================
+template <bool BF16>
+__global__ void layer_norm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, uint4* __restrict__ out, int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int V = C >> 3;
+  const uint4* xr = x + (size_t)warp * V;
+  float sum = 0.f;
+  for (int v = lane; v < V; v += 32) {
+    float f[8];
+    unpack8<BF16>(__ldg(xr + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += f[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+  for (int v = lane; v < V; v += 32) {
+    float f[8];
+    unpack8<BF16>(__ldg(xr + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; sq += d * d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  uint4* orow = out + (size_t)warp * V;
+  for (int v = lane; v < V; v += 32) {
+    float f[8];
+    unpack8<BF16>(__ldg(xr + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
+    orow[v] = pack8<BF16>(f);
+  }
+}
+
+int layer_norm_launch(const void* x, const float* gamma, const float* beta, void* out, int rows, int c, float eps,
+                      bool bf16, cudaStream_t s) {
+  if (c % 8) { set_last_error(__FILE__, __LINE__, "layer_norm: C % 8"); return -1; }
+  const int blocks = (rows + 3) / 4;
+  if (bf16) layer_norm_kernel<true><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
+  else layer_norm_kernel<false><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
+// gathers
+// =============================================================================================================
+__global__ void im2col3x3_kernel(const uint4* __restrict__ x, uint4* __restrict__ A, int n, int H, int W, int C, int Ho,
+                                 int Wo, int stride, int pad_lo, int kpad) {
+  const int KV = kpad >> 3;
+  const size_t total = (size_t)n * Ho * Wo * KV;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int kv = (int)(idx % KV);
+    const size_t m = idx / KV;
+    const int k = kv * 8;
+    const int tap = k / C, c = k - tap * C;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (tap < 9) {
+      const int wo = (int)(m % Wo);
+      const int ho = (int)((m / Wo) % Ho);
+      const int img = (int)(m / ((size_t)Wo * Ho));
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const int hi = ho * stride + dy - pad_lo, wi = wo * stride + dx - pad_lo;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __ldg(x + (((size_t)img * H + hi) * W + wi) * (C >> 3) + (c >> 3));
+    }
+    A[idx] = val;
+  }
+}
+
+int im2col3x3_launch(const void* x, void* A, int n, int H, int W, int C, int Ho, int Wo, int stride, int pad_lo,
+                     int kpad, bool, cudaStream_t s) {
+  if (C % 8 || kpad % 8) { set_last_error(__FILE__, __LINE__, "im2col: alignment"); return -1; }
+  const size_t total = (size_t)n * Ho * Wo * (kpad / 8);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+  im2col3x3_kernel<<<blocks, 256, 0, s>>>((const uint4*)x, (uint4*)A, n, H, W, C, Ho, Wo, stride, pad_lo, kpad);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BF16>
+__global__ void im2col3x3_nchw_kernel(const void* __restrict__ x, int io_dtype, uint4* __restrict__ A, int n, int C,
+                                      int H, int W, int kpad) {
+  const size_t M = (size_t)n * H * W;
+  const size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int w = (int)(m % W), h = (int)((m / W) % H), img = (int)(m / ((size_t)W * H));
+  for (int k0 = 0; k0 < kpad; k0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      const int tap = k / C, c = k - tap * C;
+      float val = 0.f;
+      if (tap < 9) {
+        const int dy = tap / 3, dx = tap - dy * 3;
+        const int hi = h + dy - 1, wi = w + dx - 1;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = load_any(x, io_dtype, (((int64_t)img * C + c) * H + hi) * W + wi);
+      }
+      v[j] = val;
+    }
+    A[m * (kpad >> 3) + (k0 >> 3)] = pack8<BF16>(v);
+  }
+}
+
+int im2col3x3_nchw_launch(const void* x, int io_dtype, void* A, int n, int C, int H, int W, int kpad, bool bf16,
+                          cudaStream_t s) {
+  const size_t M = (size_t)n * H * W;
+  const int blocks = (int)((M + 127) / 128);
+  if (bf16) im2col3x3_nchw_kernel<true><<<blocks, 128, 0, s>>>(x, io_dtype, (uint4*)A, n, C, H, W, kpad);
+  else im2col3x3_nchw_kernel<false><<<blocks, 128, 0, s>>>(x, io_dtype, (uint4*)A, n, C, H, W, kpad);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int H, int W, int V) {
+  const size_t total = (size_t)n * 2 * H * 2 * W * V;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    size_t p = idx / V;
+    const int wo = (int)(p % (2 * W));
+    p /= 2 * W;
+    const int ho = (int)(p % (2 * H));
+    const int img = (int)(p / (2 * H));
+    out[idx] = __ldg(x + (((size_t)img * H + (ho >> 1)) * W + (wo >> 1)) * V + v);
+  }
+}
+
+int upsample2x_launch(const void* x, void* out, int n, int H, int W, int C, cudaStream_t s) {
+  const size_t total = (size_t)n * 4 * H * W * (C / 8);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+  upsample2x_kernel<<<blocks, 256, 0, s>>>((const uint4*)x, (uint4*)out, n, H, W, C / 8);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BF16>
+__global__ void nhwc_to_nchw_kernel(const typename T16<BF16>::type* __restrict__ in, int ld, void* __restrict__ out,
+                                    int io_dtype, int n, int C, int hw) {
+  const size_t total = (size_t)n * C * hw;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % hw);
+    const int c = (int)((idx / hw) % C);
+    const int img = (int)(idx / ((size_t)hw * C));
+    store_any(out, io_dtype, (int64_t)idx, T16<BF16>::to_f(in[((size_t)img * hw + p) * ld + c]));
+  }
+}
+
+int nhwc_to_nchw_launch(const void* in, int ld, void* out, int io_dtype, int n, int C, int hw, bool bf16, cudaStream_t s) {
+  const size_t total = (size_t)n * C * hw;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+  if (bf16) nhwc_to_nchw_kernel<true><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld, out, io_dtype, n, C, hw);
+  else nhwc_to_nchw_kernel<false><<<blocks, 256, 0, s>>>((const __half*)in, ld, out, io_dtype, n, C, hw);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BF16>
+__global__ void cast_rows_kernel(const void* __restrict__ src, int src_dtype, typename T16<BF16>::type* __restrict__ dst,
+                                 int64_t rows, int cols, int ldo) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    dst[r * ldo + c] = T16<BF16>::from_f(load_any(src, src_dtype, idx));
+  }
+}
+
+int cast_rows_launch(const void* src, int src_dtype, void* dst, int64_t rows, int cols, int ldo, bool bf16, cudaStream_t s) {
+  const int64_t total = rows * cols;
+  if (total == 0) return 0;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  if (bf16) cast_rows_kernel<true><<<blocks, 256, 0, s>>>(src, src_dtype, (__nv_bfloat16*)dst, rows, cols, ldo);
+  else cast_rows_kernel<false><<<blocks, 256, 0, s>>>(src, src_dtype, (__half*)dst, rows, cols, ldo);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void pad_heads_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t rows, int D, int Dpad) {
+  const int64_t total = rows * Dpad;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / Dpad;
+    const int c = (int)(idx - r * Dpad);
+    dst[idx] = c < D ? src[r * D + c] : (uint16_t)0;
+  }
+}
+
+int pad_heads_launch(const void* src, void* dst, int64_t rows, int D, int Dpad, cudaStream_t s) {
+  const int64_t total = rows * Dpad;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  pad_heads_kernel<<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, rows, D, Dpad);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
+// embeddings
+// =============================================================================================================
+template <bool BF16>
+__global__ void timestep_embedding_kernel(const void* __restrict__ t, int t_dtype, float* __restrict__ out, int m, int dim) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * half) return;
+  const int row = idx / half, j = idx - row * half;
+  const float tv = load_any(t, t_dtype, row);
+  const float freq = expf(-logf(10000.f) * (float)j / (float)half);
+  const float arg = tv * freq;
+  out[(size_t)row * dim + j] = round16<BF16>(cosf(arg));
+  out[(size_t)row * dim + half + j] = round16<BF16>(sinf(arg));
+}
+
+int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int dim, bool bf16, cudaStream_t s) {
+  const int total = m * (dim / 2);
+  const int blocks = (total + 127) / 128;
+  if (bf16) timestep_embedding_kernel<true><<<blocks, 128, 0, s>>>(t, t_dtype, out, m, dim);
+  else timestep_embedding_kernel<false><<<blocks, 128, 0, s>>>(t, t_dtype, out, m, dim);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// Each warp produces NPW output features for all M rows; lanes split K in 16-byte weight vectors.
+template <bool BF16, int MT, int NPW>
+__global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, const uint4* __restrict__ W,
+                                     const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ out,
+                                     int ldo, int M, int N, int K, int silu_in) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n0 = warp * NPW;
+  if (n0 >= N) return;
+  const int KV = K >> 3;
+  for (int m0 = 0; m0 < M; m0 += MT) {
+    float acc[NPW][MT];
+#pragma unroll
+    for (int i = 0; i < NPW; ++i)
+#pragma unroll
+      for (int r = 0; r < MT; ++r) acc[i][r] = 0.f;
+    for (int kv = lane; kv < KV; kv += 32) {
+      float w[NPW][8];
+#pragma unroll
+      for (int i = 0; i < NPW; ++i) {
+        if (n0 + i < N) unpack8<BF16>(__ldg(W + (size_t)(n0 + i) * KV + kv), w[i]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[i][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < MT; ++r) {
+        if (m0 + r < M) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8 + 4));
+          float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          if (silu_in) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = round16<BF16>(silu_f(a[j]));
+          }
+#pragma unroll
+          for (int i = 0; i < NPW; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][r] = fmaf(a[j], w[i][j], acc[i][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NPW; ++i)
+#pragma unroll
+      for (int r = 0; r < MT; ++r) {
+        float v = acc[i][r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && n0 + i < N && m0 + r < M) {
+          v = round16<BF16>(v + (b ? __ldg(b + n0 + i) : 0.f));
+          if (add) v = round16<BF16>(v + add[(size_t)(m0 + r) * ldo + n0 + i]);
+          out[(size_t)(m0 + r) * ldo + n0 + i] = v;
+        }
+      }
+  }
+}
+
+int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
+                         int M, int N, int K, bool silu_in, bool bf16, cudaStream_t s) {
+  if (K % 8 || ldi % 4) { set_last_error(__FILE__, __LINE__, "skinny_linear: K % 8"); return -1; }
+  constexpr int MT = 8, NPW = 2;
+  const int warps = (N + NPW - 1) / NPW;
+  const int blocks = (warps + 3) / 4;
+  if (bf16)
+    skinny_linear_kernel<true, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_in ? 1 : 0);
+  else
+    skinny_linear_kernel<false, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_in ? 1 : 0);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BF16>
+__global__ void cast_to_f32_kernel(const void* __restrict__ src, int src_dtype, float* __restrict__ dst, int64_t n, int r16) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = load_any(src, src_dtype, i);
+    dst[i] = r16 ? round16<BF16>(v) : v;
+  }
+}
+
+int cast_to_f32_launch(const void* src, int src_dtype, float* dst, int64_t n, bool r16, bool bf16, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
+  if (bf16) cast_to_f32_kernel<true><<<blocks, 256, 0, s>>>(src, src_dtype, dst, n, r16 ? 1 : 0);
+  else cast_to_f32_kernel<false><<<blocks, 256, 0, s>>>(src, src_dtype, dst, n, r16 ? 1 : 0);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
+// weight repack
+// =============================================================================================================
+template <bool BF16>
+__global__ void pack_weight_kernel(const void* __restrict__ src, int src_dtype, typename T16<BF16>::type* __restrict__ dst,
+                                   int mode, int rows, int cols, int ld, int tile) {
+  // `cols` = logical K of the destination row (CONV3: 9 * Cin)
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / cols), k = (int)(idx - (int64_t)r * cols);
+    int64_t si;
+    if (mode == PACK_CONV3) {
+      const int cin = cols / 9;
+      const int tap = k / cin, c = k - tap * cin;
+      si = ((int64_t)r * cin + c) * 9 + tap;  // [Cout, Cin, 3, 3]
+    } else if (mode == PACK_GEGLU) {
+      const int half_rows = rows / 2, half_tile = tile / 2;
+      const int t = r / tile, rr = r - t * tile;
+      const int sr = rr < half_tile ? t * half_tile + rr : half_rows + t * half_tile + (rr - half_tile);
+      si = (int64_t)sr * cols + k;
+    } else {
+      si = idx;
+    }
+    dst[(int64_t)r * ld + k] = T16<BF16>::from_f(load_any(src, src_dtype, si));
+  }
+}
+
+int pack_weight_launch(const void* src, int src_dtype, void* dst, int mode, int rows, int cols, int ld, int tile,
+                       bool bf16, cudaStream_t s) {
+  const int64_t total = (int64_t)rows * cols;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  if (bf16) pack_weight_kernel<true><<<blocks, 256, 0, s>>>(src, src_dtype, (__nv_bfloat16*)dst, mode, rows, cols, ld, tile);
+  else pack_weight_kernel<false><<<blocks, 256, 0, s>>>(src, src_dtype, (__half*)dst, mode, rows, cols, ld, tile);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BF16>
+__global__ void pack_vector_kernel(const void* __restrict__ src, int src_dtype, float* __restrict__ dst, int n, int tile, int r16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int si = i;
+  if (tile > 0) {
+    const int half_rows = n / 2, half_tile = tile / 2;
+    const int t = i / tile, rr = i - t * tile;
+    si = rr < half_tile ? t * half_tile + rr : half_rows + t * half_tile + (rr - half_tile);
+  }
+  float v = load_any(src, src_dtype, si);
+  dst[i] = r16 ? round16<BF16>(v) : v;
+}
+
+int pack_vector_launch(const void* src, int src_dtype, float* dst, int n, int geglu_tile, bool r16, bool bf16, cudaStream_t s) {
+  const int blocks = (n + 255) / 256;
+  if (bf16) pack_vector_kernel<true><<<blocks, 256, 0, s>>>(src, src_dtype, dst, n, geglu_tile, r16 ? 1 : 0);
+  else pack_vector_kernel<false><<<blocks, 256, 0, s>>>(src, src_dtype, dst, n, geglu_tile, r16 ? 1 : 0);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
+// sampler-step fusions (latents stay fp32, as in the reference: x comes from torch.randn fp32, modules/rng.py:19)
+// =============================================================================================================
+__global__ void denoiser_in_kernel(const float* __restrict__ x, const int32_t* __restrict__ src,
+                                   const float* __restrict__ c_in, void* __restrict__ x_in, int rows, int64_t elems,
+                                   int out_dtype) {
+  const int64_t total = rows * elems;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / elems);
+    const int64_t e = idx - r * elems;
+    store_any(x_in, out_dtype, idx, x[(int64_t)src[r] * elems + e] * c_in[r]);
+  }
+}
+
+int denoiser_in_launch(const float* x, const int32_t* src, const float* c_in, void* x_in, int rows, int64_t elems,
+                       int out_dtype, cudaStream_t s) {
+  const int64_t total = rows * elems;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  denoiser_in_kernel<<<blocks, 256, 0, s>>>(x, src, c_in, x_in, rows, elems, out_dtype);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows [0,B): cond, [B,2B): uncond.  den_r = x_b + eps_r * (-sigma_b);  out_b = den_u + (den_c - den_u) * scale
+__global__ void cfg_combine_kernel(const float* __restrict__ x, const void* __restrict__ eps,
+                                   const float* __restrict__ sigma, float scale, float* __restrict__ out, int B,
+                                   int64_t elems, int eps_dtype) {
+  const int64_t total = B * elems;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / elems);
+    const float xv = x[idx], c_out = -sigma[b];
+    const float dc = xv + load_any(eps, eps_dtype, idx) * c_out;
+    const float du = xv + load_any(eps, eps_dtype, idx + total) * c_out;
+    out[idx] = du + (dc - du) * scale;
+  }
+}
+
+int cfg_combine_launch(const float* x, const void* eps, const float* sigma, float cond_scale, float* denoised, int B,
+                       int64_t elems, int eps_dtype, cudaStream_t s) {
+  const int64_t total = B * elems;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  cfg_combine_kernel<<<blocks, 256, 0, s>>>(x, eps, sigma, cond_scale, denoised, B, elems, eps_dtype);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void euler_a_step_kernel(float* __restrict__ x, const float* __restrict__ den, const float* __restrict__ noise,
+                                    float inv_sigma, float dt, float sigma_up, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float d = (xv - den[i]) * inv_sigma;
+    float r = xv + d * dt;
+    if (noise) r += noise[i] * sigma_up;
+    x[i] = r;
+  }
+}
+
+int euler_a_step_launch(float* x, const float* den, const float* noise, float sigma, float sigma_down, float sigma_up,
+                        int64_t total, cudaStream_t s) {
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  euler_a_step_kernel<<<blocks, 256, 0, s>>>(x, den, sigma_up > 0.f ? noise : nullptr, 1.f / sigma, sigma_down - sigma,
+                                             sigma_up, total);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void dpmpp_2m_step_kernel(float* __restrict__ x, const float* __restrict__ den, const float* __restrict__ old,
+                                     float ratio, float neg_expm1, float c0, float c1, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float dd = c0 * den[i];
+    if (old) dd += c1 * old[i];
+    x[i] = ratio * x[i] + neg_expm1 * dd;
+  }
+}
+
+int dpmpp_2m_step_launch(float* x, const float* den, const float* old, float ratio, float neg_expm1, float c0, float c1,
+                         int64_t total, cudaStream_t s) {
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  dpmpp_2m_step_kernel<<<blocks, 256, 0, s>>>(x, den, c1 != 0.f ? old : nullptr, ratio, neg_expm1, c0, c1, total);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sdxe
