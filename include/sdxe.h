@@ -56,6 +56,7 @@ typedef struct sdxe_config {
   int32_t context_dim;          /* 768 / 2048 */
   int32_t use_linear_in_transformer; /* 0: conv1x1 proj_in/out (SD1.x), 1: Linear (SDXL) */
   int32_t adm_in_channels;      /* 0 or 2816 (SDXL label_emb) */
+  int32_t transformer_depth_middle; /* middle block depth (SD1.x: 1, SDXL: 10) */
   /* VAE decoder */
   int32_t vae_ch;               /* 128 */
   int32_t vae_z_channels;       /* 4 */

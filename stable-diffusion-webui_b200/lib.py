@@ -38,6 +38,7 @@ class SdxeConfig(ctypes.Structure):
         ("context_dim", c_int32),
         ("use_linear_in_transformer", c_int32),
         ("adm_in_channels", c_int32),
+        ("transformer_depth_middle", c_int32),
         ("vae_ch", c_int32),
         ("vae_z_channels", c_int32),
         ("vae_out_ch", c_int32),
