@@ -269,6 +269,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   }
 }
 
+int attention_init() {
+  static bool done = false;
+  if (!done) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done = true;
+  }
+  return 0;
+}
+
 int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   AttnArgs a = a_in;
   if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {
@@ -282,11 +292,7 @@ int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   if (a.num_slots < 2) { set_last_error(__FILE__, __LINE__, "attention: smem"); return -1; }
   const size_t smem = (size_t)(q_slabs + a.num_slots + 2) * SLAB_BYTES + 8 * (2 * a.num_slots + 5) + 16 + 1024;
   auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[bf16 ? 1 : 0]) {
-    SDXE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[bf16 ? 1 : 0] = true;
-  }
+  if (attention_init() != 0) return -1;
   dim3 grid((a.Nq + 127) / 128, a.B * a.H);
   kern<<<grid, ATT_THREADS, smem, stream>>>(a);
   SDXE_CUDA_CHECK(cudaGetLastError());

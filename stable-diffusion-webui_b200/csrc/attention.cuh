@@ -21,5 +21,6 @@ struct alignas(64) AttnArgs {
 };
 
 int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
+int attention_init();
 
 }  // namespace sdxe

@@ -108,10 +108,8 @@ int sdxe_conv3x3_nhwc(const void* x, const void* w, void* out, int n, int h, int
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!is16(dtype) || cin % 64 || cout % 8) { set_last_error(__FILE__, __LINE__, "sdxe_conv3x3: alignment"); return -2; }
   const bool bf16 = dtype == SDXE_BF16;
-  if (wd > 128 || 128 % wd != 0) { set_last_error(__FILE__, __LINE__, "sdxe_conv3x3: W must divide 128"); return -2; }
-  const int bh = std::min(h, 128 / wd);
-  if (h % bh) { set_last_error(__FILE__, __LINE__, "sdxe_conv3x3: H tile"); return -2; }
-  const int bn = 128 / (wd * bh);
+  int bw, bh, bn;
+  if (!conv_tile_shape(h, wd, &bw, &bh, &bn)) { set_last_error(__FILE__, __LINE__, "sdxe_conv3x3: unsupported H x W tile"); return -2; }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.M = n * h * wd; a.N = cout; a.K = 9 * cin; a.K1 = a.K;
@@ -119,7 +117,7 @@ int sdxe_conv3x3_nhwc(const void* x, const void* w, void* out, int n, int h, int
   a.epi = EPI_PLAIN;
   a.BN = gemm_pick_bn(a.M, a.N, a.K, a.epi);
   a.num_stages = gemm_pick_stages(a.BN);
-  if (make_tmap_nhwc(&a.tmA, x, n, h, wd, cin, wd, bh, bn)) return -1;
+  if (make_tmap_nhwc(&a.tmA, x, n, h, wd, cin, bw, bh, bn)) return -1;
   a.tmA2 = a.tmA;
   if (make_tmap_2d(&a.tmB, w, cout, a.K, a.K, a.BN)) return -1;
   a.bias = bias;

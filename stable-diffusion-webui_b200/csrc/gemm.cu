@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int m0 = m_blk * BLOCK_M;
-        int img0 = 0, h0 = 0;
+        int img0 = 0, h0 = 0, w0 = 0;
         if (a.conv) {
           const int hw = a.H * a.W;
           img0 = m0 / hw;
-          h0 = (m0 % hw) / a.W;
+          const int rem = m0 - img0 * hw;
+          h0 = rem / a.W;
+          w0 = rem - h0 * a.W;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           if (a.conv) {
             const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
             const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, dx - 1, h0 + dy - 1, img0);
+            tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
           } else {
             const int k0 = kb * BLOCK_K;
             if (k0 < a.K1) tma_load_2d(sA, &a.tmA, fb, k0, m0);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
-      if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.N;
+      if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv;
 
       if (a.epi == EPI_GEGLU) {
         const int half = BN >> 1;
@@ -274,6 +276,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   }
 }
 
+bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn) {
+  if (W >= 128) {
+    if (W % 128) return false;
+    *bw = 128; *bh = 1; *bn = 1;
+    return true;
+  }
+  if (128 % W) return false;
+  const int rows = 128 / W;
+  if (H >= rows) {
+    if (H % rows) return false;
+    *bw = W; *bh = rows; *bn = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  *bw = W; *bh = H; *bn = rows / H;
+  return true;
+}
+
 int gemm_pick_stages(int BN) {
   const int stage_bytes = A_STAGE_BYTES + BN * 128;
   int s = (200 * 1024) / stage_bytes;
@@ -299,6 +319,16 @@ int gemm_pick_bn(int M, int N, int K, int epi) {
   return best_bn;
 }
 
+int gemm_init() {
+  static bool done = false;
+  if (!done) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done = true;
+  }
+  return 0;
+}
+
 int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.BN % 16 != 0 || a.BN < 16 || a.BN > 256) { set_last_error(__FILE__, __LINE__, "gemm: bad BN"); return -1; }
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
@@ -309,12 +339,8 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   const int tiles = num_m * num_n;
   if (tiles <= 0) return 0;
   const int grid = std::min(tiles, num_sms());
-  static bool attr_done[2] = {false, false};
   auto kern = bf16 ? gemm_kernel<true> : gemm_kernel<false>;
-  if (!attr_done[bf16 ? 1 : 0]) {
-    SDXE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[bf16 ? 1 : 0] = true;
-  }
+  if (gemm_init() != 0) return -1;
   kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
   SDXE_CUDA_CHECK(cudaGetLastError());
   return 0;

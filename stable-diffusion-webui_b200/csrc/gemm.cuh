@@ -20,10 +20,10 @@ struct alignas(64) GemmArgs {
   int num_stages;
   int conv;          // 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 NHWC implicit GEMM
   int cblocks;       // conv: Cin / 64
-  int H, W;          // conv: image size; tile = bn images x bh rows x W (bw == W)
+  int H, W;          // conv: image size; tile = bn images x bh rows x bw pixels (bw == W, or 128 | W)
   int bh, bn;
   int epi;
-  int relu_dummy;    // reserved
+  int ldrv;          // row pitch (elements) of rowvec
   const float* bias;    // [N] (EPI_GEGLU: interleaved like the weights) or null
   const float* rowvec;  // [M / rows_per_sample, N] per-sample vector added to every row of the sample, or null
   int rows_per_sample;
@@ -38,8 +38,11 @@ struct alignas(64) GemmArgs {
 
 // Launch on `stream`. bf16 selects the 16-bit format of A/B/out/residual. Returns 0 / -1.
 int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream);
+int gemm_init();  // one-time kernel attribute setup (call before any stream capture)
 // Tile-width heuristic: pick BN for an [M, N] output (geglu needs BN % 32 == 0 and N % BN == 0).
 int gemm_pick_bn(int M, int N, int K, int epi);
 int gemm_pick_stages(int BN);
+// 128-pixel tile of the implicit-GEMM conv as a TMA box (bw x bh x bn); false if (H, W) needs the im2col path.
+bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn);
 
 }  // namespace sdxe

@@ -1,0 +1,216 @@
+"""Python handles over the C-ABI engine objects (include/sdxe.h): UNetEngine and VAEDecoderEngine.
+
+Torch supplies device memory and the current stream; all arithmetic runs in libsdxe.so. Weights are ingested by their
+ldm state-dict keys, so the same checkpoint dict that `shared.sd_model.model.diffusion_model`
+exposes in the webui loads here unchanged (modules/sd_unet.py:54: the plugin must own its weights).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+
+
+@dataclass
+class UNetSpec:
+    """Constructor arguments of ldm / sgm UNetModel (configs/v1-inference.yaml:29-44, configs/sd_xl_inpaint.yaml:19-37)."""
+
+    in_channels: int = 4
+    out_channels: int = 4
+    model_channels: int = 320
+    channel_mult: List[int] = field(default_factory=lambda: [1, 2, 4, 4])
+    num_res_blocks: int = 2
+    transformer_depth: List[int] = field(default_factory=lambda: [1, 1, 1, 0])
+    num_heads: int = 8
+    num_head_channels: int = -1
+    context_dim: int = 768
+    use_linear_in_transformer: bool = False
+    adm_in_channels: int = 0
+    middle_depth: int = 1
+
+    @staticmethod
+    def sd15() -> "UNetSpec":
+        return UNetSpec()
+
+    @staticmethod
+    def sdxl() -> "UNetSpec":
+        return UNetSpec(channel_mult=[1, 2, 4], transformer_depth=[0, 2, 10], num_heads=-1, num_head_channels=64,
+                        context_dim=2048, use_linear_in_transformer=True, adm_in_channels=2816, middle_depth=10)
+
+    @staticmethod
+    def from_any(cfg) -> "UNetSpec":
+        """Accepts any object with the same attribute names (e.g. a parsed webui yaml or a test config)."""
+        return UNetSpec(**{k: (list(getattr(cfg, k)) if isinstance(getattr(cfg, k), (list, tuple)) else getattr(cfg, k))
+                           for k in UNetSpec.__dataclass_fields__})
+
+
+@dataclass
+class VAESpec:
+    """ddconfig of AutoencoderKL (configs/v1-inference.yaml:46-65)."""
+
+    ch: int = 128
+    out_ch: int = 3
+    ch_mult: List[int] = field(default_factory=lambda: [1, 2, 4, 4])
+    num_res_blocks: int = 2
+    z_channels: int = 4
+
+    @staticmethod
+    def from_any(cfg) -> "VAESpec":
+        return VAESpec(**{k: (list(getattr(cfg, k)) if isinstance(getattr(cfg, k), (list, tuple)) else getattr(cfg, k))
+                          for k in VAESpec.__dataclass_fields__})
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise L.SdxeError("engine dtype must be torch.float16 or torch.bfloat16")
+    return L.torch_dtype_code(dtype)
+
+
+class _EngineBase:
+    def __init__(self, cfg: L.SdxeConfig, dtype: torch.dtype, device):
+        if not torch.cuda.is_available():
+            raise L.SdxeError("no CUDA device: the sdxe engine has no CPU path")
+        self.lib = L.load()
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sdxe_create(ctypes.byref(cfg), ctypes.byref(self._h)), "sdxe_create")
+        self.finalized = False
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            with torch.cuda.device(self.device):
+                self.lib.sdxe_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weight(self, key: str, tensor: torch.Tensor):
+        t = tensor.detach()
+        if t.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            t = t.float()
+        t = t.contiguous()
+        shape = (ctypes.c_int64 * max(1, t.ndim))(*t.shape)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sdxe_set_weight(self._h, key.encode(), L.ptr(t), L.torch_dtype_code(t.dtype), t.ndim, shape),
+                    f"sdxe_set_weight({key})")
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "", only: Optional[tuple] = None):
+        """Ingest every tensor whose key starts with `prefix` (stripped), e.g. "model.diffusion_model." or
+        "first_stage_model."; `only` optionally restricts to sub-prefixes."""
+        n = 0
+        for k, v in sd.items():
+            if not k.startswith(prefix):
+                continue
+            kk = k[len(prefix):]
+            if only is not None and not kk.startswith(only):
+                continue
+            self.set_weight(kk, v)
+            n += 1
+        return n
+
+    def param_count(self) -> int:
+        return int(self.lib.sdxe_param_count(self._h))
+
+    def finalize(self):
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sdxe_finalize(self._h), "sdxe_finalize")
+        self.finalized = True
+
+    def weight_blob(self) -> torch.Tensor:
+        """The packed weight blob as a uint8 torch view (for the single NCCL broadcast at load)."""
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        L.check(self.lib.sdxe_weight_blob(self._h, ctypes.byref(p), ctypes.byref(n)), "sdxe_weight_blob")
+        return _as_tensor(p.value, n.value, self.device)
+
+
+def _as_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:
+    """uint8 tensor aliasing device memory [ptr, ptr+nbytes) via __cuda_array_interface__."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=device)
+
+
+class UNetEngine(_EngineBase):
+    def __init__(self, spec: UNetSpec, dtype: torch.dtype = torch.float16, device="cuda:0"):
+        cfg = L.SdxeConfig()
+        cfg.kind = L.SDXE_MODEL_UNET
+        cfg.dtype = _dtype_code(dtype)
+        cfg.in_channels, cfg.out_channels, cfg.model_channels = spec.in_channels, spec.out_channels, spec.model_channels
+        cfg.num_levels = len(spec.channel_mult)
+        for i, m in enumerate(spec.channel_mult):
+            cfg.channel_mult[i] = m
+            cfg.transformer_depth[i] = spec.transformer_depth[i]
+        cfg.num_res_blocks = spec.num_res_blocks
+        cfg.num_heads = spec.num_heads if spec.num_heads and spec.num_heads > 0 else 0
+        cfg.num_head_channels = spec.num_head_channels if spec.num_head_channels and spec.num_head_channels > 0 else 0
+        cfg.context_dim = spec.context_dim
+        cfg.use_linear_in_transformer = 1 if spec.use_linear_in_transformer else 0
+        cfg.adm_in_channels = spec.adm_in_channels
+        cfg.transformer_depth_middle = spec.middle_depth
+        self.spec = spec
+        super().__init__(cfg, dtype, device)
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor, y: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """eps = UNet(x, t, context[, y]); all tensors share x.dtype (fp16 / bf16 / fp32), x is [n,4,h,w] NCHW."""
+        if not x.is_cuda:
+            raise L.SdxeError("sdxe UNet needs CUDA tensors: there is no CPU fallback")
+        dt = x.dtype
+        x = x.contiguous()
+        t = timesteps.to(dt).contiguous()
+        ctx = context.to(dt).contiguous()
+        yy = y.to(dt).contiguous() if y is not None else None
+        n, _, h, w = x.shape
+        if out is None:
+            out = torch.empty_like(x)
+        L.check(self.lib.sdxe_unet_forward(self._h, L.ptr(x), L.ptr(t), L.ptr(ctx), L.ptr(yy), L.ptr(out), n, h, w,
+                                           ctx.shape[1], L.torch_dtype_code(dt), L.current_stream()), "sdxe_unet_forward")
+        return out
+
+    __call__ = forward
+
+
+class VAEDecoderEngine(_EngineBase):
+    def __init__(self, spec: VAESpec, dtype: torch.dtype = torch.float16, device="cuda:0"):
+        cfg = L.SdxeConfig()
+        cfg.kind = L.SDXE_MODEL_VAE_DECODER
+        cfg.dtype = _dtype_code(dtype)
+        cfg.num_levels = len(spec.ch_mult)
+        for i, m in enumerate(spec.ch_mult):
+            cfg.channel_mult[i] = m
+        cfg.num_res_blocks = spec.num_res_blocks
+        cfg.vae_ch, cfg.vae_z_channels, cfg.vae_out_ch = spec.ch, spec.z_channels, spec.out_ch
+        self.spec = spec
+        super().__init__(cfg, dtype, device)
+
+    def load_state_dict(self, sd, prefix: str = "", only=("decoder.", "post_quant_conv.")):
+        return super().load_state_dict(sd, prefix, only)
+
+    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """AutoencoderKL.decode(z): z [n,4,h,w] (already / scale_factor) -> [n,3,8h,8w], same dtype as z."""
+        if not z.is_cuda:
+            raise L.SdxeError("sdxe VAE needs CUDA tensors: there is no CPU fallback")
+        z = z.contiguous()
+        n, _, h, w = z.shape
+        up = 2 ** (len(self.spec.ch_mult) - 1)
+        if out is None:
+            out = torch.empty(n, self.spec.out_ch, h * up, w * up, dtype=z.dtype, device=z.device)
+        L.check(self.lib.sdxe_vae_decode(self._h, L.ptr(z), L.ptr(out), n, h, w, L.torch_dtype_code(z.dtype),
+                                         L.current_stream()), "sdxe_vae_decode")
+        return out
+
+    __call__ = decode
