@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the txt2img hot path (CFG denoising loop + VAE decode), the metric BASELINE.json names.
+
+  python bench.py --gpus N --steps K --warmup W [--config sd15|sdxl] [--dtype bf16|fp16] [--impl sdxe|reference]
+
+One "step" = one pass of the hot path over one batch: `process_images` of B images (SD1.5: 512x512, 20 Euler-a
+sampler steps, B=8 — BASELINE configs[1]; SDXL: 1024x1024, 30 DPM++ 2M Karras steps, B=4 — configs[2]) on random-init
+weights of the exact architecture and synthetic conditioning. N>1: one process per GPU (torchrun), images sharded one
+block per rank, ONE NCCL broadcast of the packed weight blob at load, no per-step collective (weak scaling).
+
+The JSON line carries: `value` (inputs resident in HBM, result left on the device), `e2e` (same call with pinned HOST
+conditioning copied in and uint8 images copied out inside the timed region), `roofline` of the dominant kernel class
+(tcgen05 GEMM / implicit-GEMM conv; per-launch CUDA-event timing from one extra instrumented pass right after the timed
+region), `cpu_baseline` (oracle = the reference's `--use-cpu all --no-half` arithmetic on the host cores, bounded
+sample), `torch_sdp_gpu` (the reference's default-SDP GPU path restated in PyTorch, same box, same run) and `clocks`.
+`--impl reference` times only the CPU reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic work (BASELINE.md §2 / SURVEY §8(d)): 2*MAC over conv / linear / QK^T / PV, no padding, no recompute
+TFLOP = {
+    "sd15": {"unet_sample": 0.8033, "vae": 2.515, "per_image": 34.65},
+    "sdxl": {"unet_sample": 6.761, "vae": 10.47, "per_image": 416.1},
+}
+WORKLOADS = {
+    "sd15": dict(name="SD1.5 txt2img 512x512, 20 Euler-a steps, batch 8 per GPU", width=512, height=512, steps=20,
+                 sampler="Euler a", batch=8, ctx_dim=768, adm=0),
+    "sdxl": dict(name="SDXL-base txt2img 1024x1024, 30 DPM++ 2M Karras steps, batch 4 per GPU", width=1024, height=1024,
+                 steps=30, sampler="DPM++ 2M", batch=4, ctx_dim=2048, adm=2816),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops_sustained=d.get("bf16_tflops_sustained", 1400.0), tflops_burst=d.get("bf16_tflops", 1590.0),
+                    hbm_gbs=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the oracle (= reference arithmetic) on the host cores, fp32, bounded sample
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(config: str, budget_note=True) -> dict:
+    """SD1.5: one CFG UNet call (2 x 64x64 samples = one Euler-a step of ONE image) + one 512x512 VAE decode, timed;
+    images/s is extrapolated as 1 / (steps * t_step + t_decode) and labelled as such. SDXL: same at 128x128 / 1024."""
+    from oracle.synth import init_module_
+    from oracle.unet import UNetModel, sd15_config, sdxl_config
+    from oracle.vae import AutoencoderKLDecode, VAEConfig
+
+    w = WORKLOADS[config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = sd15_config() if config == "sd15" else sdxl_config()
+    h, wd = w["height"] // 8, w["width"] // 8
+    with torch.no_grad():
+        unet = UNetModel(cfg).eval()          # default torch init is fine for timing (dense fp32 math either way)
+        x = torch.randn(2, 4, h, wd)
+        t = torch.tensor([500.0, 500.0])
+        ctx = torch.randn(2, 77, w["ctx_dim"])
+        y = torch.randn(2, w["adm"]) if w["adm"] else None
+        t0 = time.perf_counter()
+        unet(x, t, context=ctx, y=y)
+        t_step = time.perf_counter() - t0
+        del unet
+        vae = AutoencoderKLDecode(VAEConfig()).eval()
+        z = torch.randn(1, 4, h, wd)
+        t0 = time.perf_counter()
+        vae.decode(z)
+        t_dec = time.perf_counter() - t0
+    ips = 1.0 / (w["steps"] * t_step + t_dec)
+    return {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"1 CFG UNet call (2 samples, {t_step:.2f} s) + 1 VAE decode ({t_dec:.2f} s), fp32 torch CPU, "
+                      f"extrapolated to {w['steps']} steps/image", "t_step_s": t_step, "t_decode_s": t_dec}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.config]
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):  # each step is a bounded sample; keep the whole run to minutes
+        r = cpu_reference_sample(args.config)
+        vals.append(r)
+    best = max(vals, key=lambda r: r["value"])
+    line = {"impl": "reference", "metric": f"images/sec {w['name']}", "value": best["value"], "unit": "images/sec",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * w["batch"] / best["value"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "note": "reference --use-cpu all --no-half arithmetic (oracle port), host cores"},
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": best["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_model(config: str, dtype, device, rank: int, world: int):
+    """Random-init weights of the exact architecture. Rank 0 generates + repacks; the other ranks ingest uninitialised
+    tensors (same packing => same blob layout) and receive the blob through one NCCL broadcast."""
+    from sdwebui_b200 import checkpoint as C
+    from sdwebui_b200 import parallel as P
+    from sdwebui_b200.engine import UNetSpec, VAEDecoderEngine, VAESpec
+    from sdwebui_b200.processing import SdModel
+    from sdwebui_b200.sd_unet import SdxeUnet
+
+    spec = UNetSpec.sd15() if config == "sd15" else UNetSpec.sdxl()
+    ushapes, vshapes = C.unet_param_shapes(spec), C.vae_decoder_param_shapes(VAESpec())
+    if rank == 0:
+        usd = C.synthetic_state_dict(ushapes, seed=0, device=device, dtype=torch.float16)
+        vsd = C.synthetic_state_dict(vshapes, seed=1, device=device, dtype=torch.float16)
+    else:
+        usd, vsd = C.empty_state_dict(ushapes, device), C.empty_state_dict(vshapes, device)
+    unet = SdxeUnet(usd, spec, dtype=dtype, device=device)
+    unet.activate()
+    vae = VAEDecoderEngine(VAESpec(), dtype=dtype, device=device)
+    vae.load_state_dict(vsd)
+    vae.finalize()
+    del usd, vsd
+    torch.cuda.empty_cache()
+    bcast_bytes = 0
+    if world > 1:
+        for eng in (unet.engine, vae):
+            blob = eng.weight_blob()
+            P.broadcast_weight_blob(blob, src=0)
+            bcast_bytes += blob.numel()
+        torch.cuda.synchronize()
+    model = SdModel(unet, vae, is_sdxl=(config == "sdxl"), dtype_unet=dtype, device=device)
+    return model, bcast_bytes
+
+
+def make_conds(w, B, device, seed):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.randn(B, 77, w["ctx_dim"], generator=g)
+    u = torch.randn(B, 77, w["ctx_dim"], generator=g)
+    if w["adm"]:
+        return {"crossattn": c, "vector": torch.randn(B, w["adm"], generator=g)}, {"crossattn": u, "vector": torch.randn(B, w["adm"], generator=g)}
+    return c, u
+
+
+def to_dev(c, device, non_blocking=True):
+    if isinstance(c, dict):
+        return {k: v.to(device, non_blocking=non_blocking) for k, v in c.items()}
+    return c.to(device, non_blocking=non_blocking)
+
+
+def pin(c):
+    if isinstance(c, dict):
+        return {k: v.pin_memory() for k, v in c.items()}
+    return c.pin_memory()
+
+
+def nbytes(c):
+    if isinstance(c, dict):
+        return sum(v.numel() * v.element_size() for v in c.values())
+    return c.numel() * c.element_size()
+
+
+def torch_sdp_gpu_baseline(config, device, B, iters=2):
+    """The reference's default-SDP GPU path restated in PyTorch (oracle under fp16 autocast + SDPA, per-image VAE
+    decode), same box, same workload; random torch-init weights (timing only)."""
+    from oracle.pipeline import OraclePipeline, SamplingParams
+    from oracle.unet import UNetModel, sd15_config, sdxl_config
+    from oracle.vae import AutoencoderKLDecode, VAEConfig
+
+    w = WORKLOADS[config]
+    cfg = sd15_config() if config == "sd15" else sdxl_config()
+    with torch.device(device):
+        unet = UNetModel(cfg).half().eval()
+        vae = AutoencoderKLDecode(VAEConfig()).half().eval()
+    pipe = OraclePipeline(unet, vae, device, dtype_unet=torch.float16, dtype_vae=torch.float16, autocast=True)
+    c, u = make_conds(w, B, device, 5)
+    c, u = to_dev(c, device), to_dev(u, device)
+    sp = SamplingParams(sampler=w["sampler"], steps=w["steps"], width=w["width"], height=w["height"],
+                        seeds=tuple(range(1000, 1000 + B)), randn_source="GPU", scale_factor=0.13025 if config == "sdxl" else 0.18215)
+    kw = dict(y_cond=c["vector"], y_uncond=u["vector"]) if isinstance(c, dict) else {}
+    cc, uu = (c["crossattn"], u["crossattn"]) if isinstance(c, dict) else (c, u)
+    pipe.txt2img(sp, cc, uu, **kw)  # warm-up (cuDNN autotune etc.)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        pipe.txt2img(sp, cc, uu, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    del pipe, unet, vae
+    torch.cuda.empty_cache()
+    return {"value": B / (ms / 1000.0), "unit": "images/sec", "ms_per_step": ms,
+            "how": "oracle restatement under torch.autocast(fp16) + F.scaled_dot_product_attention, per-image VAE decode"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sdxe", choices=["sdxe", "reference"])
+    ap.add_argument("--config", default=os.environ.get("SDXE_BENCH_CONFIG", "sd15"), choices=["sd15", "sdxl"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / torch-SDP legs")
+    args = ap.parse_args()
+
+    from sdwebui_b200 import parallel as P
+
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl sdxe needs a CUDA device (no CPU fallback)")
+    rank, world, local = P.init_from_env("nccl" if world_env > 1 else None)
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    import torch.distributed as dist
+
+    from sdwebui_b200 import lib as L
+    from sdwebui_b200.processing import StableDiffusionProcessingTxt2Img, process_images
+
+    w = WORKLOADS[args.config]
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    B = w["batch"]
+    model, bcast_bytes = build_model(args.config, dtype, device, rank, world)
+    lib = L.load()
+    seeds = [1000 + rank * B + i for i in range(B)]  # global image index -> seed: sharding is invisible in the output
+    c_host, u_host = make_conds(w, B, device, 7 + rank)
+    c_host, u_host = pin(c_host), pin(u_host)
+    c_dev, u_dev = to_dev(c_host, device, False), to_dev(u_host, device, False)
+
+    def make_p(c, u, **kw):
+        return StableDiffusionProcessingTxt2Img(sd_model=model, c=c, uc=u, seeds=seeds, sampler_name=w["sampler"], steps=w["steps"],
+                                                cfg_scale=7.0, width=w["width"], height=w["height"], randn_source="GPU", **kw)
+
+    def step_resident():
+        return process_images(make_p(c_dev, u_dev), to_host=False)
+
+    def step_e2e():
+        return process_images(make_p(to_dev(c_host, device), to_dev(u_host, device)), to_host=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.sdxe_launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=device)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = tms.item()
+        return ms, lib.sdxe_launch_count() - n0
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(step_resident, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    n_img = B * world * args.steps
+    value = n_img / (ms_res / 1000.0)
+    e2e = n_img / (ms_e2e / 1000.0)
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- roofline of the dominant kernel class: one instrumented UNet call (2B CFG batch) + one VAE decode batch
+        unet_e, vae_e = model.unet.engine, model.vae
+        h, wd = w["height"] // 8, w["width"] // 8
+        x = torch.randn(2 * B, 4, h, wd, device=device, dtype=dtype)
+        t = torch.full((2 * B,), 500.0, device=device, dtype=dtype)
+        ctx = torch.randn(2 * B, 77, w["ctx_dim"], device=device, dtype=dtype)
+        y = torch.randn(2 * B, w["adm"], device=device, dtype=dtype) if w["adm"] else None
+        unet_e.profile(True)
+        unet_e.forward(x, t, ctx, y)
+        torch.cuda.synchronize()
+        prof_u = unet_e.profile_read()
+        unet_e.profile(False)
+        vae_e.profile(True)
+        vae_e.decode(torch.randn(B, 4, h, wd, device=device, dtype=dtype))
+        torch.cuda.synchronize()
+        prof_v = vae_e.profile_read()
+        vae_e.profile(False)
+        mm_ms = prof_u["gemm"]["ms"] + prof_u["conv3x3"]["ms"]
+        mm_fl = prof_u["gemm"]["flops"] + prof_u["conv3x3"]["flops"]
+        mm_n = prof_u["gemm"]["launches"] + prof_u["conv3x3"]["launches"]
+        achieved = mm_fl / (mm_ms / 1000.0) / 1e12 if mm_ms > 0 else 0.0
+        total_u = sum(v["ms"] for v in prof_u.values())
+        roofline = {"bound": "tensor", "kernel": "sdxe::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved,
+                    "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                    "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)", "traffic": None,
+                    "launches_per_unet_call": mm_n, "avg_launch_us": 1000.0 * mm_ms / max(1, mm_n),
+                    "share_of_unet_call": mm_ms / total_u if total_u else None,
+                    "how": "CUDA events around every launch of one extra instrumented UNet call on the launching stream "
+                           "(sdxe_profile), algorithmic 2*M*N*K per launch",
+                    "by_kernel_class_unet": {k: {"ms": round(v["ms"], 4), "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else 0),
+                                                 "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0), "launches": v["launches"]}
+                                             for k, v in prof_u.items()},
+                    "by_kernel_class_vae": {k: {"ms": round(v["ms"], 4), "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else 0),
+                                                "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0), "launches": v["launches"]}
+                                            for k, v in prof_v.items()},
+                    "whole_job_frac": value * TFLOP[args.config]["per_image"] / (world * peaks["tflops_sustained"])}
+        extras = {}
+        if not args.no_extras:
+            try:
+                extras["torch_sdp_gpu"] = torch_sdp_gpu_baseline(args.config, device, B)
+            except Exception as ex:  # noqa: BLE001
+                extras["torch_sdp_gpu"] = {"unavailable": repr(ex)[:200]}
+            try:
+                cb = cpu_reference_sample(args.config)
+                extras["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as ex:  # noqa: BLE001
+                extras["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port", "sample": repr(ex)[:200]}
+        h2d = nbytes(c_host) + nbytes(u_host)
+        d2h = B * w["height"] * w["width"] * 3
+        line = {"metric": f"images/sec {w['name']}", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world} (image shards, no per-step collective)",
+                           "l2": "working set (>= 1.7 GB weights + activations) >> 126 MB L2: no explicit flush",
+                           "weights": "random-init, exact architecture", "weight_broadcast_bytes": bcast_bytes},
+                "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,12 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
 /* image = AutoencoderKL.decode(z): z [n, 4, h, w] (already divided by scale_factor) -> [n, 3, 8h, 8w] NCHW. */
 int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int w, int io_dtype, void* stream);
 
+/* Per-kernel-class timing: while enabled, forward / decode calls run their plan eagerly with a CUDA event pair
+ * around every launch on the launching stream. kind: 0 GEMM (tcgen05), 1 conv3x3 implicit GEMM (tcgen05),
+ * 2 attention, 3 GroupNorm, 4 LayerNorm, 5 other. flops / bytes are ALGORITHMIC totals of the timed launches. */
+int sdxe_profile(sdxe_engine* e, int enable);
+int sdxe_profile_read(sdxe_engine* e, int kind, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* out[b, q, h*D + j] = softmax(q k^T * scale) v.  q: [B,H,Nq,D], k,v: [B,H,Nk,D] contiguous, 16-bit `dtype`;
  * out: [B, Nq, H*D]. D multiple of 8, D <= 512. */
 int sdxe_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int D,

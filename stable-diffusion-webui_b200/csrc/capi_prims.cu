@@ -134,7 +134,7 @@ int sdxe_group_norm_nhwc(const void* x, const float* gamma, const float* beta, v
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!is16(dtype)) { set_last_error(__FILE__, __LINE__, "group_norm: dtype"); return -2; }
   float* stats = nullptr;
-  SDXE_CUDA_CHECK(cudaMallocAsync((void**)&stats, sizeof(float) * 2 * groups * n, stream));
+  SDXE_CUDA_CHECK(cudaMallocAsync((void**)&stats, sizeof(float) * group_norm_scratch_floats(n, groups), stream));
   int rc = group_norm_launch(x, c, nullptr, 0, gamma, beta, out, stats, n, hw, groups, eps, silu != 0, dtype == SDXE_BF16, stream);
   cudaFreeAsync(stats, stream);
   return rc;

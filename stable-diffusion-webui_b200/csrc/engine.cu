@@ -148,6 +148,9 @@ struct sdxe_engine {
   std::map<std::string, std::unique_ptr<Plan>> plans;
   cudaStream_t cap_stream = nullptr;
   bool use_graph = true;
+  bool profiling = false;
+  double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0};
+  int64_t prof_launches[8] = {0};
 
   ~sdxe_engine();
   // --- weights
@@ -172,9 +175,22 @@ struct sdxe_engine {
 
 namespace {
 
+using OpFn = std::function<int(cudaStream_t)>;
+enum : int { K_GEMM = 0, K_CONV = 1, K_ATTN = 2, K_GNORM = 3, K_LNORM = 4, K_OTHER = 5, K_NUM = 6 };
+struct OpRec {
+  OpFn fn;
+  int kind = K_OTHER;
+  double flops = 0, bytes = 0;  // algorithmic work of this launch
+  OpRec() {}
+  template <class F>
+  OpRec(F f) : fn(std::move(f)) {}  // implicit: un-annotated ops are K_OTHER
+  template <class F>
+  OpRec(F f, int k, double fl, double by) : fn(std::move(f)), kind(k), flops(fl), bytes(by) {}
+};
+
 struct Plan {
   sdxe_engine* e = nullptr;
-  std::vector<std::function<int(cudaStream_t)>> pre, body, post;
+  std::vector<OpRec> pre, body, post;
   cudaGraphExec_t gexec = nullptr;
   cudaGraph_t graph = nullptr;
   // per-call caller pointers, read by pre / post ops
@@ -194,7 +210,7 @@ struct Builder {
   sdxe_engine* e;
   Plan* plan;
   bool bf16;
-  std::vector<std::function<int(cudaStream_t)>>* ops;
+  std::vector<OpRec>* ops;
 
   Builder(sdxe_engine* e_, Plan* p) : e(e_), plan(p), bf16(e_->bf16), ops(&p->body) {}
 
@@ -243,7 +259,10 @@ struct Builder {
     a.heads = o.heads; a.head_dim = o.head_dim; a.head_pad = o.head_pad; a.tokens = o.tokens;
     for (int i = 0; i < 3; ++i) a.outs[i] = o.outs[i];
     const bool b = bf16;
-    ops->push_back([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); });
+    const double nout = (o.epi == EPI_GEGLU) ? W.N / 2.0 : (double)W.N;
+    const double by = 2.0 * ((double)M * W.K + (double)W.N * W.K + (double)M * nout + (o.residual ? (double)M * nout : 0.0));
+    ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); }, K_GEMM,
+                         2.0 * (double)M * W.N * W.K, by));
     return 0;
   }
 
@@ -266,7 +285,10 @@ struct Builder {
       a.residual = o.residual; a.ldr = o.ldr;
       a.out = out; a.ldo = ldo;
       const bool b = bf16;
-      ops->push_back([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); });
+      const double Md = (double)a.M;
+      const double by = 2.0 * (Md * x.c + (double)W.N * a.K + Md * W.N + (o.residual ? Md * W.N : 0.0));
+      ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); }, K_CONV,
+                           2.0 * Md * W.N * a.K, by));
       return 0;
     }
     // generic geometry: explicit im2col (still CUDA; used for odd resolutions / narrow channel counts)
@@ -293,7 +315,7 @@ struct Builder {
   int group_norm(const Act& x1, const Act* x2, const NormW& nw, float eps, bool silu, Act& out) {
     const int c2 = x2 ? x2->c : 0;
     out = new_act(x1.n, x1.h, x1.w, x1.c + c2);
-    Buf st = e->alloc(sizeof(float) * 2 * 32 * x1.n);
+    Buf st = e->alloc(sizeof(float) * group_norm_scratch_floats(x1.n, 32));
     const void *p1 = x1.p, *p2 = x2 ? x2->p : nullptr;
     void* po = out.p;
     float* sp = (float*)st.p;
@@ -301,7 +323,8 @@ struct Builder {
     const float *g = nw.g, *bt = nw.b;
     const bool b = bf16;
     if (nw.C != c1 + c2) EFAIL("group_norm: channel mismatch");
-    ops->push_back([=](cudaStream_t s) { return group_norm_launch(p1, c1, p2, c2, g, bt, po, sp, n, hw, 32, eps, silu, b, s); });
+    ops->push_back(OpRec([=](cudaStream_t s) { return group_norm_launch(p1, c1, p2, c2, g, bt, po, sp, n, hw, 32, eps, silu, b, s); },
+                         K_GNORM, 0.0, 4.0 * (double)n * hw * (c1 + c2)));
     e->release(st);
     return 0;
   }
@@ -309,7 +332,8 @@ struct Builder {
     const float *g = nw.g, *bt = nw.b;
     const int C = nw.C;
     const bool b = bf16;
-    ops->push_back([=](cudaStream_t s) { return layer_norm_launch(x, g, bt, out, (int)rows, C, 1e-5f, b, s); });
+    ops->push_back(OpRec([=](cudaStream_t s) { return layer_norm_launch(x, g, bt, out, (int)rows, C, 1e-5f, b, s); }, K_LNORM, 0.0,
+                         4.0 * (double)rows * C));
     return 0;
   }
   int attention(const void* q, const void* k, const void* v, int B, int H, int Nq, int Nk, int d, int dpad, int ldq,
@@ -330,7 +354,9 @@ struct Builder {
       a.scale_log2 = scale * 1.4426950408889634f;
       a.out = out; a.ldo = ldo; a.out_col0 = v0;
       const bool b = bf16;
-      ops->push_back([a, b](cudaStream_t s) { count_launch(); return attention_launch(a, b, s); });
+      const double fl = 2.0 * (double)B * H * Nq * Nk * ((double)d + dv);
+      const double by = 2.0 * (double)B * H * ((double)Nq * d + (double)Nk * (d + dv) + (double)Nq * dv);
+      ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return attention_launch(a, b, s); }, K_ATTN, fl, by));
     }
     return 0;
   }
@@ -800,14 +826,19 @@ void sdxe_engine::release_heads(void* p, int bh, int tokens, int d, int dpad, co
 // =================================================================================================================
 namespace {
 
-int run_ops(std::vector<std::function<int(cudaStream_t)>>& ops, cudaStream_t s) {
-  for (auto& f : ops) ECHK(f(s));
+int run_ops(std::vector<OpRec>& ops, cudaStream_t s) {
+  for (auto& r : ops) ECHK(r.fn(s));
   return 0;
 }
 
+// Profiling pass: every body op bracketed by CUDA events on the launching stream (eager, no graph).
+int run_ops_profiled(sdxe_engine* e, std::vector<OpRec>& ops, cudaStream_t s);
+
 int run_plan(sdxe_engine* e, Plan* p, cudaStream_t stream) {
   ECHK(run_ops(p->pre, stream));
-  if (e->use_graph) {
+  if (e->profiling) {
+    ECHK(run_ops_profiled(e, p->body, stream));
+  } else if (e->use_graph) {
     if (!p->gexec) {
       // capture the body once on a private stream, then replay on the caller's stream
       if (!e->cap_stream) SDXE_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
@@ -830,6 +861,32 @@ int run_plan(sdxe_engine* e, Plan* p, cudaStream_t stream) {
   }
   ECHK(run_ops(p->post, stream));
   return 0;
+}
+
+int run_ops_profiled(sdxe_engine* e, std::vector<OpRec>& ops, cudaStream_t s) {
+  const size_t n = ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& x : ev) SDXE_CUDA_CHECK(cudaEventCreate(&x));
+  int rc = 0;
+  SDXE_CUDA_CHECK(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n && rc == 0; ++i) {
+    rc = ops[i].fn(s);
+    cudaEventRecord(ev[i + 1], s);
+  }
+  cudaStreamSynchronize(s);
+  if (rc == 0) {
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      const int k = ops[i].kind;
+      e->prof_ms[k] += ms;
+      e->prof_flops[k] += ops[i].flops;
+      e->prof_bytes[k] += ops[i].bytes;
+      e->prof_launches[k] += 1;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
 }
 
 // ---- UNet plan -----------------------------------------------------------------------------------------------
@@ -1112,7 +1169,7 @@ int sdxe_create(const sdxe_config* cfg, sdxe_engine** out) {
   e->cfg = *cfg;
   e->bf16 = cfg->dtype == SDXE_BF16;
   e->dt = cfg->dtype;
-  if (gemm_init() != 0 || attention_init() != 0) { delete e; return -1; }
+  if (gemm_init() != 0 || attention_init() != 0 || kernels_init() != 0) { delete e; return -1; }
   const char* ng = getenv("SDXE_NO_GRAPH");
   e->use_graph = !(ng && ng[0] == '1');
   *out = e;
@@ -1200,6 +1257,21 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
   Plan* p = it->second.get();
   p->x = x; p->t = t; p->ctx = ctx; p->y = y; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
+}
+
+int sdxe_profile(sdxe_engine* e, int enable) {
+  if (!e) EFAIL("sdxe_profile: null");
+  e->profiling = enable != 0;
+  if (enable) {
+    for (int k = 0; k < 8; ++k) { e->prof_ms[k] = e->prof_flops[k] = e->prof_bytes[k] = 0; e->prof_launches[k] = 0; }
+  }
+  return 0;
+}
+
+int sdxe_profile_read(sdxe_engine* e, int kind, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!e || kind < 0 || kind >= K_NUM) EFAIL("sdxe_profile_read: bad argument");
+  *ms = e->prof_ms[kind]; *flops = e->prof_flops[kind]; *bytes = e->prof_bytes[kind]; *launches = e->prof_launches[kind];
+  return 0;
 }
 
 int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int w, int io_dtype, void* stream) {

@@ -49,47 +49,65 @@ SDXE_DEVINL float round16(float v) { return T16<BF16>::to_f(T16<BF16>::from_f(v)
 // =============================================================================================================
 // GroupNorm (ldm GroupNorm32: statistics in fp32 — modules/devices.py:284-295 states the upcast)
 // =============================================================================================================
+// Deterministic two-level reduction (no atomics: the same input always gives bit-identical statistics, as the
+// reference's torch.group_norm does): block partials [n, chunk, group, 2] -> finalize -> (mean, rstd) per (n, group).
 template <bool BF16>
 __global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
-                                float* __restrict__ stats, int hw, int groups, int pix_per_block) {
-  extern __shared__ float gs[];  // [2 * groups]
+                                float* __restrict__ partial, int hw, int groups, int pix_per_block) {
+  extern __shared__ float sh[];  // [rpi][C] sums, then [rpi][C] sums of squares
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int n = blockIdx.y;
   const int vec = threadIdx.x % V, prow = threadIdx.x / V, rpi = blockDim.x / V;
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) gs[i] = 0.f;
-  __syncthreads();
+  float* sh_s = sh;
+  float* sh_q = sh + rpi * C;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   const int c = vec * 8;
-  if (prow < rpi) {
-    for (int p = p0 + prow; p < p1; p += rpi) {
-      const size_t pix = (size_t)n * hw + p;
-      const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
-      float v[8];
-      unpack8<BF16>(u, v);
+  for (int p = p0 + prow; p < p1; p += rpi) {
+    const size_t pix = (size_t)n * hw + p;
+    const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
+    float v[8];
+    unpack8<BF16>(u, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      atomicAdd(&gs[2 * g], s[j]);
-      atomicAdd(&gs[2 * g + 1], ss[j]);
-    }
+    for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh_s[prow * C + c + j] = s[j]; sh_q[prow * C + c + j] = ss[j]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * groups + i], gs[i]);
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rpi; ++r)
+      for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) { a += sh_s[r * C + cc]; b += sh_q[r * C + cc]; }
+    float* dst = partial + (((size_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int n_img, int chunks,
+                                   int groups, float inv_cnt, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * groups) return;
+  const int n = i / groups, g = i - n * groups;
+  float a = 0.f, b = 0.f;
+  for (int ch = 0; ch < chunks; ++ch) {
+    const float* src = partial + (((size_t)n * chunks + ch) * groups + g) * 2;
+    a += src[0];
+    b += src[1];
+  }
+  const float mean = a * inv_cnt;
+  const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
 template <bool BF16, bool SILU>
 __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, uint4* __restrict__ out, int n_img, int hw, int groups,
-                                float eps) {
+                                const float* __restrict__ beta, uint4* __restrict__ out, int n_img, int hw, int groups) {
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
-  const float inv_cnt = 1.f / ((float)hw * (float)cpg);
   const size_t total = (size_t)n_img * hw * V;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int vec = (int)(idx % V);
@@ -105,10 +123,8 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cpg;
       if (g != g_prev) {
-        const float sm = stats[((size_t)n * groups + g) * 2], sq = stats[((size_t)n * groups + g) * 2 + 1];
-        mean = sm * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        rstd = rsqrtf(var + eps);
+        mean = __ldg(stats + ((size_t)n * groups + g) * 2);
+        rstd = __ldg(stats + ((size_t)n * groups + g) * 2 + 1);
         g_prev = g;
       }
       float y = (v[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
@@ -119,31 +135,49 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint
   }
 }
 
+int kernels_init() {
+  static bool done = false;
+  if (!done) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    done = true;
+  }
+  return 0;
+}
+
+size_t group_norm_scratch_floats(int n, int groups) { return (size_t)n * groups * 2 * ((size_t)num_sms() * 4 + 2); }
+
 int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* out,
-                      float* stats, int n, int hw, int groups, float eps, bool silu, bool bf16, cudaStream_t s) {
+                      float* scratch, int n, int hw, int groups, float eps, bool silu, bool bf16, cudaStream_t s) {
   if (x2 == nullptr) c2 = 0;
   const int C = c1 + c2;
   if (C % 8 || c1 % 8 || C % groups) { set_last_error(__FILE__, __LINE__, "group_norm: channel alignment"); return -1; }
   const int V = C / 8;
   if (V > 1024) { set_last_error(__FILE__, __LINE__, "group_norm: too many channels"); return -1; }
-  SDXE_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, s));
-  const int rpi = std::max(1, 256 / V);
+  int rpi = std::max(1, 256 / V);
+  while (rpi > 1 && (size_t)rpi * C * 8 > 96 * 1024) --rpi;
   const int threads = V * rpi;
   int chunks = std::max(1, std::min((num_sms() * 4 + n - 1) / n, (hw + rpi * 4 - 1) / (rpi * 4)));
   const int ppb = (hw + chunks - 1) / chunks;
   chunks = (hw + ppb - 1) / ppb;
+  float* stats = scratch;                          // [n, groups, 2] (mean, rstd)
+  float* partial = scratch + (size_t)n * groups * 2;  // [n, chunks, groups, 2]
   dim3 grid(chunks, n);
-  const size_t sm = sizeof(float) * 2 * groups;
+  const size_t sm = sizeof(float) * 2 * rpi * C;
+  if (kernels_init() != 0) return -1;
   if (bf16)
-    gn_stats_kernel<true><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, hw, groups, ppb);
+    gn_stats_kernel<true><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb);
   else
-    gn_stats_kernel<false><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, hw, groups, ppb);
+    gn_stats_kernel<false><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb);
+  SDXE_LAUNCH_CHECK();
+  const float inv_cnt = 1.f / ((float)hw * (float)(C / groups));
+  gn_finalize_kernel<<<(n * groups + 127) / 128, 128, 0, s>>>(partial, stats, n, chunks, groups, inv_cnt, eps);
   SDXE_LAUNCH_CHECK();
   const size_t total = (size_t)n * hw * V;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
 #define GN_APPLY(B, S)                                                                                              \
   gn_apply_kernel<B, S><<<blocks, 256, 0, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, gamma, beta, \
-                                               (uint4*)out, n, hw, groups, eps)
+                                               (uint4*)out, n, hw, groups)
   if (bf16) { if (silu) GN_APPLY(true, true); else GN_APPLY(true, false); }
   else { if (silu) GN_APPLY(false, true); else GN_APPLY(false, false); }
 #undef GN_APPLY

@@ -7,9 +7,11 @@ namespace sdxe {
 // ---- normalisation ---------------------------------------------------------------------------------------
 // GroupNorm over NHWC 16-bit activations; the input may be the channel-concatenation of two tensors
 // (x1: [n,hw,c1], x2: [n,hw,c2] or null) — this is how the UNet's skip-concat is consumed without a torch.cat.
-// stats: [n, groups, 2] fp32 scratch (sum, sumsq), zeroed by the call.
+// scratch: fp32 [group_norm_scratch_floats(n, groups)] (block partials + final mean / rstd); no atomics, deterministic.
+size_t group_norm_scratch_floats(int n, int groups);
+int kernels_init();  // one-time kernel attribute setup (before any stream capture)
 int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* out,
-                      float* stats, int n, int hw, int groups, float eps, bool silu, bool bf16, cudaStream_t s);
+                      float* scratch, int n, int hw, int groups, float eps, bool silu, bool bf16, cudaStream_t s);
 int layer_norm_launch(const void* x, const float* gamma, const float* beta, void* out, int rows, int c, float eps,
                       bool bf16, cudaStream_t s);
 

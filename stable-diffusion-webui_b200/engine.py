@@ -126,6 +126,21 @@ class _EngineBase:
             L.check(self.lib.sdxe_finalize(self._h), "sdxe_finalize")
         self.finalized = True
 
+    PROFILE_KINDS = ("gemm", "conv3x3", "attention", "group_norm", "layer_norm", "other")
+
+    def profile(self, enable: bool):
+        L.check(self.lib.sdxe_profile(self._h, 1 if enable else 0), "sdxe_profile")
+
+    def profile_read(self) -> dict:
+        """{kind: {"ms", "flops", "bytes", "launches"}} accumulated since profile(True)."""
+        out = {}
+        for k, name in enumerate(self.PROFILE_KINDS):
+            ms, fl, by, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+            L.check(self.lib.sdxe_profile_read(self._h, k, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by), ctypes.byref(n)),
+                    "sdxe_profile_read")
+            out[name] = {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
+        return out
+
     def weight_blob(self) -> torch.Tensor:
         """The packed weight blob as a uint8 torch view (for the single NCCL broadcast at load)."""
         p, n = ctypes.c_void_p(), ctypes.c_int64()

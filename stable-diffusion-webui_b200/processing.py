@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference pipeline boundary for the accelerated path (boundary A):
+
+  StableDiffusionProcessingTxt2Img     modules/processing.py:1166-1555  (fields used on the hot path only)
+  process_images(p) -> Processed       modules/processing.py:819-1112
+  decode_latent_batch                  modules/processing.py:625-672
+  SdModel.apply_model                  LatentDiffusion.apply_model as patched by modules/sd_hijack_unet.py:40-54
+                                       (+ DiffusionWrapper, modules/models/diffusion/ddpm_edit.py:1417-1437;
+                                        SDXL: modules/sd_models_xl.py:37-43)
+
+Text encoders, PNG/infotext, scripts and the UI are outside the accelerated path: conditionings arrive as tensors
+(what `p.setup_conds()` leaves in p.c / p.uc), images leave as a uint8 tensor.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import lib as L
+from . import samplers as S
+from .engine import VAEDecoderEngine
+from .rng import ImageRNG
+from .sd_unet import SdxeUnet
+
+opt_C, opt_f = 4, 8  # modules/processing.py:39-40
+
+
+class SdModel:
+    """What the hot path needs of `shared.sd_model`: the (replacement) UNet, the VAE decoder, the noise schedule."""
+
+    def __init__(self, unet: SdxeUnet, vae: Optional[VAEDecoderEngine], is_sdxl: bool, dtype_unet=torch.float16,
+                 device="cuda:0", scale_factor: Optional[float] = None):
+        self.unet = unet
+        self.vae = vae
+        self.is_sdxl = is_sdxl
+        self.dtype_unet = dtype_unet
+        self.dtype_vae = dtype_unet
+        self.device = torch.device(device)
+        self.scale_factor = scale_factor if scale_factor is not None else (0.13025 if is_sdxl else 0.18215)
+        self.alphas_cumprod = S.make_alphas_cumprod().to(self.device)
+        self.parameterization = "eps"
+
+    def apply_model(self, x_noisy, t, cond=None, **kwargs):
+        """cast to dtype_unet, call the UNet through the SdUnet seam (sd_hijack_unet.py:40-54)."""
+        ctx = cond["crossattn"] if isinstance(cond, dict) else cond
+        vec = cond.get("vector") if isinstance(cond, dict) else None
+        return self.apply_model_scaled(x_noisy.to(self.dtype_unet), t, ctx, vec)
+
+    def apply_model_scaled(self, x_in, t, context, vector=None):
+        dt = self.dtype_unet
+        kwargs = {}
+        if vector is not None:
+            kwargs["y"] = vector.to(dt)
+        return self.unet.forward(x_in, t.to(dt), context.to(dt), **kwargs)
+
+    def decode_first_stage(self, z):
+        """z already divided by scale_factor upstream? No: the reference's decode_first_stage divides
+        (ddpm_edit.py:726-784: z = 1/scale_factor * z). Same here."""
+        if self.vae is None:
+            raise L.SdxeError("no VAE decoder engine attached")
+        return self.vae.decode((z.to(self.dtype_vae) / self.scale_factor).contiguous())
+
+
+@dataclass
+class StableDiffusionProcessingTxt2Img:
+    sd_model: SdModel = None
+    c: object = None                 # cond:  tensor [B,T,C] or {"crossattn","vector"} (per image)
+    uc: object = None                # uncond, same form
+    seeds: List[int] = field(default_factory=lambda: [1000])
+    sampler_name: str = "Euler a"
+    scheduler: str = "Automatic"
+    steps: int = 20
+    cfg_scale: float = 7.0
+    width: int = 512
+    height: int = 512
+    eta: Optional[float] = None
+    s_noise: float = 1.0
+    s_min_uncond: float = 0.0
+    randn_source: str = "GPU"
+    enable_hr: bool = False
+    hr_scale: float = 2.0
+    hr_second_pass_steps: int = 0
+    denoising_strength: float = 0.75
+    do_not_decode: bool = False
+    batch_size: int = 0
+    rng: ImageRNG = None
+    sampler: S.KDiffusionSampler = None
+    is_hr_pass: bool = False
+
+    def __post_init__(self):
+        self.batch_size = len(self.seeds)
+
+    # modules/processing.py:1307-1362
+    def sample(self, conditioning, unconditional_conditioning, seeds):
+        self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
+        x = self.rng.next()
+        samples = self.sampler.sample(self, x, conditioning, unconditional_conditioning)
+        if not self.enable_hr:
+            return samples
+        return self.sample_hr_pass(samples, seeds)
+
+    # modules/processing.py:1364-1463, latent upscale mode "Latent" (bilinear, antialias False: shared.py:54-56)
+    def sample_hr_pass(self, samples, seeds):
+        self.is_hr_pass = True
+        tw, th = int(self.width * self.hr_scale), int(self.height * self.hr_scale)
+        samples = torch.nn.functional.interpolate(samples, size=(th // opt_f, tw // opt_f), mode="bilinear", antialias=False)
+        shape = (opt_C, th // opt_f, tw // opt_f)
+        self.rng = ImageRNG(shape, seeds, source=self.randn_source, device=self.sd_model.device)
+        noise = self.rng.next()
+        self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
+        return self.sampler.sample_img2img(self, samples, noise, self.c, self.uc, steps=self.hr_second_pass_steps or self.steps)
+
+
+@dataclass
+class Processed:
+    images: torch.Tensor = None      # uint8 [B, H, W, 3] on the host (what becomes PIL images in the reference)
+    latents: torch.Tensor = None     # final latents fp32 [B,4,h,w] (device)
+    seeds: List[int] = None
+
+
+def decode_latent_batch(model: SdModel, batch: torch.Tensor, target_device=None, check_for_nans=False, batched=True):
+    """modules/processing.py:625-672. The reference decodes one image at a time; the engine takes the whole batch in
+    one call (`batched=True`) — per-sample GroupNorm/attention make the results identical either way."""
+    if check_for_nans and bool(torch.isnan(batch.view(-1)[0])):
+        raise L.SdxeError("A tensor with all NaNs was produced in Unet.")  # devices.test_for_nans contract
+    if batched:
+        out = model.decode_first_stage(batch)
+    else:
+        out = torch.cat([model.decode_first_stage(batch[i:i + 1]) for i in range(batch.shape[0])])
+    if check_for_nans and bool(torch.isnan(out.view(-1)[0])):
+        raise L.SdxeError("A tensor with all NaNs was produced in VAE.")
+    return out if target_device is None else out.to(target_device)
+
+
+@torch.no_grad()
+def process_images(p: StableDiffusionProcessingTxt2Img, to_host: bool = True) -> Processed:
+    """process_images_inner (modules/processing.py:863-1091) for one batch (`n_iter` == 1)."""
+    S.state.interrupted = False
+    S.state.skipped = False
+    dev = p.sd_model.device
+    with torch.cuda.device(dev):
+        p.rng = ImageRNG((opt_C, p.height // opt_f, p.width // opt_f), p.seeds, source=p.randn_source, device=dev)
+        samples = p.sample(p.c, p.uc, p.seeds)
+        if p.do_not_decode:
+            return Processed(None, samples, list(p.seeds))
+        x = decode_latent_batch(p.sd_model, samples, check_for_nans=False)
+        x = torch.clamp((x.float() + 1.0) / 2.0, min=0.0, max=1.0)                         # processing.py:1004-1005
+        img = (x.permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255).to(torch.uint8)        # :1017-1018
+        if not to_host:
+            return Processed(img, samples, list(p.seeds))
+        host = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(img, non_blocking=False)
+    return Processed(host, samples, list(p.seeds))

@@ -1,0 +1,399 @@
+"""Host-side mirror of the reference's sampler stack for the accelerated path, with the same names, argument meaning
+and error behaviour, so parity tests read like the reference's own:
+
+  KDiffusionSampler            modules/sd_samplers_kdiffusion.py:68-234  (get_sigmas / sample / sample_img2img)
+  CFGDenoiser.forward          modules/sd_samplers_cfg_denoiser.py:156-311 — signature kept:
+                               forward(x, sigma, uncond, cond, cond_scale, s_min_uncond, image_cond)
+  CompVisDenoiser              k_diffusion/external.py (un-vendored; constructed at sd_samplers_kdiffusion.py:61-62)
+  sample_euler_ancestral,
+  sample_dpmpp_2m              k_diffusion/sampling.py (un-vendored; selected at sd_samplers_kdiffusion.py:11-27)
+  setup_img2img_steps          modules/sd_samplers_common.py:22-31
+  InterruptedException         modules/sd_samplers_common.py (raised when state.interrupted, cfg_denoiser.py:157-158)
+
+What is new: the UNet behind `inner_model` is the sdxe engine, and the per-step latent-space elementwise work
+(2B batch build + c_in, x + eps*c_out + CFG combine, sampler update) runs as three fused CUDA kernels from
+libsdxe.so instead of ~15 small PyTorch launches. The sigma schedule stays on the host
+(modules/sd_samplers_kdiffusion.py:127,132).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+class InterruptedException(BaseException):
+    pass
+
+
+class SamplerState:
+    """The two cooperative-cancel flags the reference polls each denoiser call (modules/shared_state.py:79)."""
+
+    interrupted = False
+    skipped = False
+    sampling_step = 0
+    sampling_steps = 0
+
+
+state = SamplerState()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# k-diffusion schedule / denoiser wrapper
+# ------------------------------------------------------------------------------------------------------------------
+def make_alphas_cumprod(linear_start=0.00085, linear_end=0.012, timesteps=1000) -> torch.Tensor:
+    """ldm 'linear' (scaled-linear) beta schedule; configs/v1-inference.yaml:5-9, ddpm_edit.py:133-141."""
+    betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+    return torch.tensor(np.cumprod(1.0 - betas, axis=0), dtype=torch.float32)
+
+
+class DiscreteSchedule:
+    def __init__(self, alphas_cumprod: torch.Tensor, device):
+        self.sigmas = (((1 - alphas_cumprod) / alphas_cumprod) ** 0.5).to(device)
+        self.log_sigmas = self.sigmas.log()
+
+    def get_sigmas(self, n: int) -> torch.Tensor:
+        t_max = len(self.sigmas) - 1
+        t = torch.linspace(t_max, 0, n, device=self.sigmas.device)
+        return torch.cat([self.t_to_sigma(t), t.new_zeros([1])])
+
+    def sigma_to_t(self, sigma: torch.Tensor) -> torch.Tensor:
+        log_sigma = sigma.log()
+        dists = log_sigma - self.log_sigmas[:, None]
+        low_idx = dists.ge(0).cumsum(dim=0).argmax(dim=0).clamp(max=self.log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = self.log_sigmas[low_idx], self.log_sigmas[high_idx]
+        w = ((low - log_sigma) / (low - high)).clamp(0, 1)
+        t = (1 - w) * low_idx + w * high_idx
+        return t.view(sigma.shape)
+
+    def t_to_sigma(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.float()
+        low_idx, high_idx, w = t.floor().long(), t.ceil().long(), t.frac()
+        return ((1 - w) * self.log_sigmas[low_idx] + w * self.log_sigmas[high_idx]).exp()
+
+
+class CompVisDenoiser(DiscreteSchedule):
+    """eps-prediction wrapper: D(x, sigma) = x + eps(x * c_in, t(sigma)) * c_out."""
+
+    sigma_data = 1.0
+
+    def __init__(self, sd_model, quantize: bool = False):
+        super().__init__(sd_model.alphas_cumprod, sd_model.device)
+        self.inner_model = sd_model
+        if quantize:
+            raise NotImplementedError("enable_quantization is off by default (shared_options.py:176) and not mirrored")
+
+    def get_scalings(self, sigma):
+        return -sigma, 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+
+    def forward(self, x, sigma, **kwargs):
+        c_out, c_in = [s.view(-1, 1, 1, 1) for s in self.get_scalings(sigma)]
+        eps = self.inner_model.apply_model(x * c_in, self.sigma_to_t(sigma), **kwargs)
+        return x + eps * c_out
+
+    __call__ = forward
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    ramp = torch.linspace(0, 1, n, device=device)
+    min_inv_rho, max_inv_rho = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
+def setup_img2img_steps(p, steps=None):
+    """modules/sd_samplers_common.py:22-31 (img2img_fix_steps is off by default)."""
+    if steps is not None:
+        requested = steps or p.steps
+        steps = int(requested / min(p.denoising_strength, 0.999)) if p.denoising_strength > 0 else 0
+        t_enc = requested - 1
+    else:
+        steps = p.steps
+        t_enc = int(min(p.denoising_strength, 0.999) * steps)
+    return steps, t_enc
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CFG denoiser
+# ------------------------------------------------------------------------------------------------------------------
+def _cond_tensor(c):
+    return c["crossattn"] if isinstance(c, dict) else c
+
+
+class CFGDenoiser:
+    """Classifier-free-guidance denoiser with the reference's call signature. `cond` / `uncond` are the per-step
+    reconstructed conditionings: a tensor [B, T, C] or, for SDXL, a dict {"crossattn": [B,T,C], "vector": [B,2816]}
+    (what prompt_parser.reconstruct_*_batch returns, modules/prompt_parser.py:280-349). One cond per image."""
+
+    def __init__(self, sampler):
+        self.sampler = sampler
+        self.model_wrap = None
+        self.mask = None
+        self.nmask = None
+        self.init_latent = None
+        self.steps = None
+        self.total_steps = None
+        self.step = 0
+        self.image_cfg_scale = None
+        self.p = None
+        self.mask_before_denoising = False
+        self.cond_scale_miltiplier = 1.0
+        self._src = {}
+        self.on_cfg_denoiser = []   # callables(x_in, sigma_in, cond_in) -> None   (script_callbacks.on_cfg_denoiser)
+        self.on_cfg_denoised = []   # callables(x_out)                              (on_cfg_denoised)
+        self.on_cfg_after_cfg = []  # callables(denoised) -> denoised | None        (on_cfg_after_cfg)
+
+    @property
+    def inner_model(self):
+        if self.model_wrap is None:
+            self.model_wrap = CompVisDenoiser(self.sampler.sd_model, quantize=False)
+        return self.model_wrap
+
+    def combine_denoised(self, x_out, conds_list, uncond, cond_scale):
+        """sd_samplers_cfg_denoiser.py:74-82 (general form, torch ops)."""
+        denoised_uncond = x_out[-uncond.shape[0]:]
+        denoised = torch.clone(denoised_uncond)
+        for i, conds in enumerate(conds_list):
+            for cond_index, weight in conds:
+                denoised[i] += (x_out[cond_index] - denoised_uncond[i]) * (weight * cond_scale)
+        return denoised
+
+    def _apply_blend(self, latent):
+        return latent * self.nmask + self.init_latent * self.mask
+
+    def forward(self, x, sigma, uncond, cond, cond_scale, s_min_uncond, image_cond):
+        if state.interrupted or state.skipped:
+            raise InterruptedException
+        model = self.inner_model
+        sd = self.sampler.sd_model
+        lib = L.load()
+        if self.mask_before_denoising and self.mask is not None:
+            x = self._apply_blend(x)
+        B = x.shape[0]
+        c_t, u_t = _cond_tensor(cond), _cond_tensor(uncond)
+        if c_t.shape[0] != B or u_t.shape[0] != B:
+            raise L.SdxeError("CFGDenoiser: one cond and one uncond per image expected (AND-composition is not accelerated)")
+        skip_uncond = bool((self.step % 2) and s_min_uncond > 0 and float(sigma[0]) < s_min_uncond)
+        if c_t.shape[1] != u_t.shape[1] and not skip_uncond:
+            raise L.SdxeError("CFGDenoiser: cond / uncond token counts differ; enable pad_cond_uncond upstream")
+        x = x.float().contiguous()
+        sigma = sigma.float().contiguous()
+        rows = B if skip_uncond else 2 * B
+        src = self._src.get((rows, B))
+        if src is None:
+            src = (torch.arange(rows, device=x.device, dtype=torch.int32) % B).contiguous()
+            self._src[(rows, B)] = src
+        sigma_in = sigma if skip_uncond else torch.cat([sigma, sigma])
+        cond_in = c_t if skip_uncond else torch.cat([c_t, u_t])
+        vec_in = None
+        if isinstance(cond, dict) and "vector" in cond:
+            vec_in = cond["vector"] if skip_uncond else torch.cat([cond["vector"], uncond["vector"]])
+        for cb in self.on_cfg_denoiser:
+            cb(x, sigma_in, cond_in)
+        # --- fused: x_in[r] = x[src[r]] * c_in[r] in the UNet's dtype (cfg_denoiser.py:203 + CompVisDenoiser c_in +
+        #     the dtype cast of sd_hijack_unet.py:43-50)
+        c_out, c_in = model.get_scalings(sigma_in)
+        t = model.sigma_to_t(sigma_in)
+        elems = x[0].numel()
+        x_in = torch.empty((rows,) + tuple(x.shape[1:]), dtype=sd.dtype_unet, device=x.device)
+        stream = L.current_stream()
+        L.check(lib.sdxe_denoiser_in(L.ptr(x), L.ptr(src), L.ptr(c_in.contiguous()), L.ptr(x_in), rows, elems,
+                                     L.torch_dtype_code(sd.dtype_unet), stream), "sdxe_denoiser_in")
+        eps = sd.apply_model_scaled(x_in, t, cond_in, vec_in)  # engine UNet through the SdUnet seam
+        for cb in self.on_cfg_denoised:
+            cb(eps)
+        scale = 1.0 if skip_uncond else float(cond_scale) * self.cond_scale_miltiplier
+        denoised = torch.empty_like(x)
+        if skip_uncond:
+            # denoised = x + eps * c_out (no uncond branch evaluated: cfg_denoiser.py:229-231,272-275)
+            denoised = x + eps.float() * c_out.view(-1, 1, 1, 1)
+        else:
+            L.check(lib.sdxe_cfg_combine(L.ptr(x), L.ptr(eps), L.ptr(sigma), scale, L.ptr(denoised), B, elems,
+                                         L.torch_dtype_code(eps.dtype), stream), "sdxe_cfg_combine")
+        if not self.mask_before_denoising and self.mask is not None:
+            denoised = self._apply_blend(denoised)
+        self.sampler.last_latent = denoised
+        for cb in self.on_cfg_after_cfg:
+            r = cb(denoised)
+            if r is not None:
+                denoised = r
+        self.step += 1
+        return denoised
+
+    __call__ = forward
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sampler loops (k_diffusion.sampling restated; the update itself is one fused kernel per step)
+# ------------------------------------------------------------------------------------------------------------------
+def get_ancestral_step(sigma_from: float, sigma_to: float, eta: float = 1.0):
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+@torch.no_grad()
+def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                           noise_sampler: Optional[Callable] = None):
+    """noise_sampler(sigma, sigma_next) -> noise like x; the webui routes it to p.rng.next() (sd_samplers_common.py:225)."""
+    extra_args = {} if extra_args is None else extra_args
+    lib = L.load()
+    x = x.float().contiguous().clone()
+    s_in = x.new_ones([x.shape[0]])
+    sig = [float(s) for s in sigmas]  # host schedule
+    for i in range(len(sig) - 1):
+        denoised = model(x, s_in * sig[i], **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        noise = None
+        if sig[i + 1] > 0:
+            noise = noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous()
+        L.check(lib.sdxe_euler_ancestral_step(L.ptr(x), L.ptr(denoised.contiguous()), L.ptr(noise), sig[i], sigma_down,
+                                              sigma_up * s_noise if sig[i + 1] > 0 else 0.0, x.numel(),
+                                              L.current_stream()), "sdxe_euler_ancestral_step")
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=None):
+    extra_args = {} if extra_args is None else extra_args
+    lib = L.load()
+    x = x.float().contiguous().clone()
+    s_in = x.new_ones([x.shape[0]])
+    sig = [float(s) for s in sigmas]
+
+    def t_fn(s):
+        return -math.log(s) if s > 0 else math.inf
+
+    old_denoised = None
+    for i in range(len(sig) - 1):
+        denoised = model(x, s_in * sig[i], **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        t, t_next = t_fn(sig[i]), t_fn(sig[i + 1])
+        h = t_next - t
+        ratio = sig[i + 1] / sig[i]
+        neg_expm1 = -math.expm1(-h) if math.isfinite(h) else 1.0
+        if old_denoised is None or sig[i + 1] == 0:
+            c0, c1 = 1.0, 0.0
+        else:
+            h_last = t - t_fn(sig[i - 1])
+            r = h_last / h
+            c0, c1 = 1 + 1 / (2 * r), -1 / (2 * r)
+        L.check(lib.sdxe_dpmpp_2m_step(L.ptr(x), L.ptr(denoised), L.ptr(old_denoised), ratio, neg_expm1, c0, c1, x.numel(),
+                                       L.current_stream()), "sdxe_dpmpp_2m_step")
+        old_denoised = denoised
+    return x
+
+
+# label, function, aliases, options — the two samplers north_star names (sd_samplers_kdiffusion.py:11-27)
+samplers_k_diffusion = [
+    ("DPM++ 2M", sample_dpmpp_2m, ["k_dpmpp_2m"], {"scheduler": "karras"}),
+    ("Euler a", sample_euler_ancestral, ["k_euler_a", "k_euler_ancestral"], {"uses_ensd": True}),
+]
+_sampler_map = {}
+for _label, _fn, _aliases, _opts in samplers_k_diffusion:
+    _sampler_map[_label.lower()] = (_label, _fn, _opts)
+    for _a in _aliases:
+        _sampler_map[_a.lower()] = (_label, _fn, _opts)
+_sampler_map["dpm++ 2m karras"] = _sampler_map["dpm++ 2m"]  # pre-1.9 name (infotext compatibility)
+
+
+class KDiffusionSampler:
+    def __init__(self, funcname_or_label, sd_model, options=None):
+        key = funcname_or_label.lower() if isinstance(funcname_or_label, str) else None
+        if key not in _sampler_map:
+            raise L.SdxeError(f"sampler {funcname_or_label!r} is not accelerated (available: Euler a, DPM++ 2M)")
+        self.label, self.func, self.options = _sampler_map[key]
+        if options:
+            self.options = {**self.options, **options}
+        self.sd_model = sd_model
+        self.model_wrap_cfg = CFGDenoiser(self)
+        self.model_wrap = self.model_wrap_cfg.inner_model
+        self.last_latent = None
+        self.eta = 1.0
+        self.s_noise = 1.0
+        self.s_min_uncond = 0.0
+        self.p = None
+        self.sampler_extra_args = None
+
+    # -- sigma schedule (sd_samplers_kdiffusion.py:79-132 with default options) --------------------------------
+    def get_sigmas(self, p, steps: int) -> torch.Tensor:
+        scheduler_name = getattr(p, "scheduler", None) or "Automatic"
+        if scheduler_name == "Automatic":
+            scheduler_name = self.options.get("scheduler", None)
+        m_sigma_min, m_sigma_max = self.model_wrap.sigmas[0].item(), self.model_wrap.sigmas[-1].item()
+        if scheduler_name is None or scheduler_name.lower() in ("uniform",):
+            sigmas = self.model_wrap.get_sigmas(steps)
+        elif scheduler_name.lower() == "karras":
+            sigmas = get_sigmas_karras(n=steps, sigma_min=m_sigma_min, sigma_max=m_sigma_max, rho=7.0, device="cpu")
+        else:
+            raise L.SdxeError(f"scheduler {scheduler_name!r} is not mirrored")
+        return sigmas.cpu()
+
+    def initialize(self, p) -> dict:
+        self.p = p
+        cfg = self.model_wrap_cfg
+        cfg.p = p
+        cfg.mask = getattr(p, "mask", None)
+        cfg.nmask = getattr(p, "nmask", None)
+        cfg.step = 0
+        self.eta = p.eta if getattr(p, "eta", None) is not None else 1.0
+        self.s_min_uncond = getattr(p, "s_min_uncond", 0.0)
+        kw = {}
+        if self.func is sample_euler_ancestral:
+            kw["eta"] = self.eta
+            kw["s_noise"] = getattr(p, "s_noise", 1.0)
+            kw["noise_sampler"] = lambda sigma, sigma_next: p.rng.next()  # TorchHijack.randn_like
+        return kw
+
+    def launch_sampling(self, steps, func):
+        self.model_wrap_cfg.steps = steps
+        self.model_wrap_cfg.total_steps = steps
+        state.sampling_steps = steps
+        state.sampling_step = 0
+        try:
+            return func()
+        except InterruptedException:
+            return self.last_latent
+
+    def callback_state(self, d):
+        state.sampling_step = d["i"]
+
+    def sample(self, p, x, conditioning, unconditional_conditioning, steps=None, image_conditioning=None):
+        steps = steps or p.steps
+        sigmas = self.get_sigmas(p, steps)
+        x = x * sigmas[0]
+        extra = self.initialize(p)
+        self.last_latent = x
+        self.sampler_extra_args = {"cond": conditioning, "image_cond": image_conditioning, "uncond": unconditional_conditioning,
+                                   "cond_scale": p.cfg_scale, "s_min_uncond": self.s_min_uncond}
+        return self.launch_sampling(steps, lambda: self.func(self.model_wrap_cfg, x, extra_args=self.sampler_extra_args,
+                                                             disable=False, callback=self.callback_state, sigmas=sigmas, **extra))
+
+    def sample_img2img(self, p, x, noise, conditioning, unconditional_conditioning, steps=None, image_conditioning=None):
+        steps, t_enc = setup_img2img_steps(p, steps)
+        sigmas = self.get_sigmas(p, steps)
+        sigma_sched = sigmas[steps - t_enc - 1:]
+        xi = x + noise * sigma_sched[0]
+        extra = self.initialize(p)
+        self.model_wrap_cfg.init_latent = x
+        self.last_latent = x
+        self.sampler_extra_args = {"cond": conditioning, "image_cond": image_conditioning, "uncond": unconditional_conditioning,
+                                   "cond_scale": p.cfg_scale, "s_min_uncond": self.s_min_uncond}
+        return self.launch_sampling(t_enc + 1, lambda: self.func(self.model_wrap_cfg, xi, extra_args=self.sampler_extra_args,
+                                                                 disable=False, callback=self.callback_state,
+                                                                 sigmas=sigma_sched, **extra))
+
+
+def create_sampler(name, model) -> KDiffusionSampler:
+    """modules/sd_samplers.py:33."""
+    return KDiffusionSampler(name, model)
