@@ -39,15 +39,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   const int q_slabs = a.q_resident ? a.dqk_slabs : 0;
   const uint32_t sQ = sbase;
   const uint32_t sRing = sQ + q_slabs * SLAB_BYTES;
-  const uint32_t sP = sRing + NS * SLAB_BYTES;
-  const uint32_t bar_base = sP + 2 * SLAB_BYTES;
+  const uint32_t sP = sRing + NS * SLAB_BYTES;   // two P tiles (double buffered), 2 slabs each
+  const uint32_t bar_base = sP + 4 * SLAB_BYTES;
   auto slot_full = [&](int s) { return bar_base + 8u * s; };
   auto slot_empty = [&](int s) { return bar_base + 8u * (NS + s); };
   const uint32_t q_full = bar_base + 8u * (2 * NS);
   auto s_full = [&](int i) { return bar_base + 8u * (2 * NS + 1 + i); };
-  const uint32_t p_ready = bar_base + 8u * (2 * NS + 3);
-  const uint32_t pv_done = bar_base + 8u * (2 * NS + 4);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 5));
+  // per-P-buffer barriers: a waiter is never more than one phase behind on any of them
+  auto p_ready = [&](int i) { return bar_base + 8u * (2 * NS + 3 + i); };
+  auto pv_done = [&](int i) { return bar_base + 8u * (2 * NS + 5 + i); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -59,8 +60,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     mbar_init(q_full, 1);
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
-    mbar_init(p_ready, 4);
-    mbar_init(pv_done, 1);
+    mbar_init(p_ready(0), 4);
+    mbar_init(p_ready(1), 4);
+    mbar_init(pv_done(0), 1);
+    mbar_init(pv_done(1), 1);
     fence_mbar_init();
     tma_prefetch_desc(&a.tmQ);
     tma_prefetch_desc(&a.tmK);
@@ -140,21 +143,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         }
         if (i >= 1) {
           const int j = i - 1;  // O += P_j V_j
-          mbar_wait(p_ready, (uint32_t)(j & 1));
+          mbar_wait(p_ready(j & 1), (uint32_t)((j >> 1) & 1));
           tc_fence_after();
+          const uint32_t sPj = sP + (uint32_t)(j & 1) * 2 * SLAB_BYTES;
           for (int vs = 0; vs < a.dv_slabs; ++vs) {
             const uint32_t v_addr = pop();
             tc_fence_after();
             const uint32_t d_o = tmem_base + TM_O + (uint32_t)(vs * 64);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const uint64_t pd = umma_desc_sw128(sP + (k >> 2) * SLAB_BYTES, 16, 1024) + 2 * (k & 3);
+              const uint64_t pd = umma_desc_sw128(sPj + (k >> 2) * SLAB_BYTES, 16, 1024) + 2 * (k & 3);
               const uint64_t vd = umma_desc_sw128(v_addr + k * 2048, SLAB_BYTES, 1024);
               tc_mma_f16(d_o, pd, vd, idesc_pv, (j | k) != 0 ? 1u : 0u);
             }
             release();
           }
-          tc_commit(pv_done);
+          tc_commit(pv_done(j & 1));
         }
       }
     }
@@ -170,25 +174,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       tc_fence_after();
       const uint32_t t_s = tmem_base + TM_S0 + (uint32_t)((i & 1) * 128) + lane_base;
       const int kv0 = i * 128;
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
+      // the whole 128-wide score row of this thread lives in registers: one TMEM round trip per block
+      uint32_t sreg[128];
+      tmem_ld32(t_s, sreg);
+      tmem_ld32(t_s + 32, sreg + 32);
+      tmem_ld32(t_s + 64, sreg + 64);
+      tmem_ld32(t_s + 96, sreg + 96);
+      tc_wait_ld();
+      if (kv0 + 128 > a.Nk) {  // only the last block has invalid key columns
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = (kv0 + c * 32 + j < a.Nk) ? __uint_as_float(r[j]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
+        for (int j = 0; j < 128; ++j)
+          if (kv0 + j >= a.Nk) sreg[j] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * sl2);  // first block: exp2(-inf) = 0
-      const float mb = m_new * sl2;
-      if (i >= 1) {
-        mbar_wait(pv_done, (uint32_t)((i - 1) & 1));  // P buffer free, O holds blocks < i
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sreg[j]));
+      // lazy rescale: keep a stale running max until it is off by more than 2^8 (p stays <= 256, exact after 1/l)
+      const float m_cand = fmaxf(m_run, mx);
+      const bool need = (m_cand - m_run) * sl2 > 8.f;  // first block: +inf > 8
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = ex2_approx((m_run - m_cand) * sl2);  // first block: 0
+        if (i >= 1) {
+          mbar_wait(pv_done((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));  // O holds every block < i
+          tc_fence_after();
           for (int c = 0; c < a.dv_slabs * 2; ++c) {
             uint32_t r[32];
             const uint32_t t_o = tmem_base + TM_O + lane_base + c * 32;
@@ -200,25 +208,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           }
           tc_wait_st();
         }
+        l_run *= alpha;
+        m_run = m_cand;
       }
+      const float mb = m_run * sl2;
+      if (i >= 2) mbar_wait(pv_done(i & 1), (uint32_t)(((i >> 1) + 1) & 1));  // P buffer (i & 1) free: PV(i-2) done
       float sum = 0.f;
-#pragma unroll 1
+      const uint32_t p_buf = sP + (uint32_t)(i & 1) * 2 * SLAB_BYTES;
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float v0 = (kv0 + c * 32 + j < a.Nk) ? __uint_as_float(r[j]) : -INFINITY;
-          const float v1 = (kv0 + c * 32 + j + 1 < a.Nk) ? __uint_as_float(r[j + 1]) : -INFINITY;
-          const float p0 = exp2f(fmaf(v0, sl2, -mb));
-          const float p1 = exp2f(fmaf(v1, sl2, -mb));
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + j]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + j + 1]), sl2, -mb));
           sum += p0 + p1;
           pk[j >> 1] = T::pack(p0, p1);
         }
         // P tile: two K-major 128B-swizzle atoms of 64 kv columns; this chunk = 4 x 16 B of row `row`
-        const uint32_t p_row = sP + (c >> 1) * SLAB_BYTES + row * 128;
+        const uint32_t p_row = p_buf + (c >> 1) * SLAB_BYTES + row * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
@@ -227,15 +235,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
                        : "memory");
         }
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
+      l_run += sum;
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(p_ready(i & 1));
     }
     // ---- epilogue: O / l -> out[b, q, h*dv + j]
-    mbar_wait(pv_done, (uint32_t)((nblk - 1) & 1));
+    mbar_wait(pv_done((nblk - 1) & 1), (uint32_t)(((nblk - 1) >> 1) & 1));
     tc_fence_after();
     const int q = q0 + row;
     const float inv_l = 1.f / l_run;
@@ -288,9 +295,9 @@ int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   a.q_resident = a.dqk_slabs <= 3 ? 1 : 0;
   const int q_slabs = a.q_resident ? a.dqk_slabs : 0;
   const int budget = (224 * 1024 - 2048) / SLAB_BYTES;  // slabs that fit beside barriers + alignment slack
-  a.num_slots = std::min(10, budget - 2 - q_slabs);
+  a.num_slots = std::min(10, budget - 4 - q_slabs);
   if (a.num_slots < 2) { set_last_error(__FILE__, __LINE__, "attention: smem"); return -1; }
-  const size_t smem = (size_t)(q_slabs + a.num_slots + 2) * SLAB_BYTES + 8 * (2 * a.num_slots + 5) + 16 + 1024;
+  const size_t smem = (size_t)(q_slabs + a.num_slots + 4) * SLAB_BYTES + 8 * (2 * a.num_slots + 7) + 16 + 1024;
   auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
   if (attention_init() != 0) return -1;
   dim3 grid((a.Nq + 127) / 128, a.B * a.H);

@@ -230,6 +230,11 @@ template <> struct T16<true> {
   static SDXE_DEVINL type from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
+SDXE_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 SDXE_DEVINL float silu_f(float x) { return x / (1.f + __expf(-x)); }
 SDXE_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
