@@ -13,16 +13,19 @@
 //               16 KB, 128B swizzle) through one in-order ring, in exactly the order the MMA warp consumes them.
 //   warp 1    : tcgen05.mma issuer.  S_i = Q K_i^T -> TMEM (double buffered);  O += P_i V_i -> TMEM.
 //               V is used as an MN-major B operand straight from its natural [kv, dv] layout.
-//   warps 2-5 : online softmax, one thread per query row (tcgen05.ld 32x32b): running max / sum in fp32,
-//               P written to shared memory in the UMMA K-major 128B-swizzle layout, O rescaled in TMEM only
-//               when a row max moved; final 1/l scaling and store.
+//   warps 2-9 : online softmax. Each query row is shared by two threads (warps w and w+4 own the same TMEM lane
+//               quarter; one takes key columns 0-63 of the block, the other 64-127) so every scheduler has two
+//               softmax warps to interleave. Row max agreed through a tiny smem exchange + 64-thread named barrier,
+//               partial row sums kept per thread and added at the end. P is written to shared memory in the UMMA
+//               K-major 128B-swizzle layout (double buffered); O is rescaled in TMEM lazily (only when the running
+//               max moved by more than 2^8); final 1/l scaling and store.
 #include "attention.cuh"
 #include <algorithm>
 
 namespace sdxe {
 
 static constexpr int SLAB_BYTES = 16384;  // 128 rows x 64 x 2 B
-static constexpr int ATT_THREADS = 192;
+static constexpr int ATT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two warps per TMEM lane quarter)
 static constexpr int TM_S0 = 0, TM_O = 256;  // TMEM columns: S buffers at 0 / 128, O at 256..511
 
 template <bool BF16>
@@ -49,6 +52,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   auto p_ready = [&](int i) { return bar_base + 8u * (2 * NS + 3 + i); };
   auto pv_done = [&](int i) { return bar_base + 8u * (2 * NS + 5 + i); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7));
+  float* xch = reinterpret_cast<float*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7) + 16);  // [2 buf][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -60,8 +64,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     mbar_init(q_full, 1);
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
-    mbar_init(p_ready(0), 4);
-    mbar_init(p_ready(1), 4);
+    mbar_init(p_ready(0), 8);
+    mbar_init(p_ready(1), 8);
     mbar_init(pv_done(0), 1);
     mbar_init(pv_done(1), 1);
     fence_mbar_init();
@@ -106,6 +110,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, 128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc(BF16 ? 1 : 0, 128, 64, 0, 1);
+      // zero-padded tails are skipped: fewer K steps on the last Q/K slab, narrower N on the last V slab
+      const int ksteps_last = (a.dqk - (a.dqk_slabs - 1) * 64 + 15) / 16;
+      const int n_last = (a.dv - (a.dv_slabs - 1) * 64 + 15) / 16 * 16;
+      const uint32_t idesc_pv_last = umma_idesc(BF16 ? 1 : 0, 128, n_last, 0, 1);
       int slot = 0;
       uint32_t phase = 0;
       auto pop = [&]() -> uint32_t {  // wait for the next slab in ring order, return its smem address
@@ -134,8 +142,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             tc_fence_after();
             const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
             const uint64_t kd = umma_desc_sw128(k_addr, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+            const int ks = (c == a.dqk_slabs - 1) ? ksteps_last : 4;
+            for (int k = 0; k < ks; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
             if (q_slot_held) { tc_commit(slot_empty(q_slot)); (void)q_phase; }
             release();
           }
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             for (int k = 0; k < 8; ++k) {
               const uint64_t pd = umma_desc_sw128(sPj + (k >> 2) * SLAB_BYTES, 16, 1024) + 2 * (k & 3);
               const uint64_t vd = umma_desc_sw128(v_addr + k * 2048, SLAB_BYTES, 1024);
-              tc_mma_f16(d_o, pd, vd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+              tc_mma_f16(d_o, pd, vd, (vs == a.dv_slabs - 1) ? idesc_pv_last : idesc_pv, (j | k) != 0 ? 1u : 0u);
             }
             release();
           }
@@ -164,40 +172,50 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     }
   } else {
     // ---------------------------------------------------------------- softmax / epilogue
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;            // TMEM lane quarter (warps w and w+4 share it)
+    const int half = (warp - 2) >> 2;        // which 64 key columns of each block this thread owns
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
+    const uint32_t pair_bar = 1u + (uint32_t)quarter;  // named barrier of the two warps sharing these 32 rows
     float m_run = -INFINITY, l_run = 0.f;
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(s_full(i & 1), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      const uint32_t t_s = tmem_base + TM_S0 + (uint32_t)((i & 1) * 128) + lane_base;
-      const int kv0 = i * 128;
-      // the whole 128-wide score row of this thread lives in registers: one TMEM round trip per block
-      uint32_t sreg[128];
+      const uint32_t t_s = tmem_base + TM_S0 + (uint32_t)((i & 1) * 128) + lane_base + (uint32_t)(half * 64);
+      const int kv0 = i * 128 + half * 64;
+      uint32_t sreg[64];
       tmem_ld32(t_s, sreg);
       tmem_ld32(t_s + 32, sreg + 32);
-      tmem_ld32(t_s + 64, sreg + 64);
-      tmem_ld32(t_s + 96, sreg + 96);
       tc_wait_ld();
-      if (kv0 + 128 > a.Nk) {  // only the last block has invalid key columns
+      if (kv0 + 64 > a.Nk) {  // only the tail of the last block has invalid key columns
 #pragma unroll
-        for (int j = 0; j < 128; ++j)
+        for (int j = 0; j < 64; ++j)
           if (kv0 + j >= a.Nk) sreg[j] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sreg[j]));
+      for (int j = 0; j < 64; j += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sreg[j]));
+        mx1 = fmaxf(mx1, __uint_as_float(sreg[j + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sreg[j + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sreg[j + 3]));
+      }
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // agree on the row max with the thread that owns the other 64 columns
+      float* xb = xch + (i & 1) * 256;
+      xb[half * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       // lazy rescale: keep a stale running max until it is off by more than 2^8 (p stays <= 256, exact after 1/l)
       const float m_cand = fmaxf(m_run, mx);
       const bool need = (m_cand - m_run) * sl2 > 8.f;  // first block: +inf > 8
-      if (__any_sync(0xffffffffu, need)) {
+      if (__any_sync(0xffffffffu, need)) {             // identical decision in both warps of the pair
         const float alpha = ex2_approx((m_run - m_cand) * sl2);  // first block: 0
         if (i >= 1) {
           mbar_wait(pv_done((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));  // O holds every block < i
           tc_fence_after();
-          for (int c = 0; c < a.dv_slabs * 2; ++c) {
+          for (int c = half * a.dv_slabs; c < (half + 1) * a.dv_slabs; ++c) {  // each half rescales its O columns
             uint32_t r[32];
             const uint32_t t_o = tmem_base + TM_O + lane_base + c * 32;
             tmem_ld32(t_o, r);
@@ -213,42 +231,46 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       }
       const float mb = m_run * sl2;
       if (i >= 2) mbar_wait(pv_done(i & 1), (uint32_t)(((i >> 1) + 1) & 1));  // P buffer (i & 1) free: PV(i-2) done
-      float sum = 0.f;
-      const uint32_t p_buf = sP + (uint32_t)(i & 1) * 2 * SLAB_BYTES;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      // this half's 64 columns = K-major 128B-swizzle atom `half` of P buffer (i & 1)
+      const uint32_t p_row = sP + (uint32_t)(i & 1) * 2 * SLAB_BYTES + (uint32_t)half * SLAB_BYTES + row * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + j]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + j + 1]), sl2, -mb));
-          sum += p0 + p1;
-          pk[j >> 1] = T::pack(p0, p1);
-        }
-        // P tile: two K-major 128B-swizzle atoms of 64 kv columns; this chunk = 4 x 16 B of row `row`
-        const uint32_t p_row = p_buf + (c >> 1) * SLAB_BYTES + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[q * 4 + 0]),
-                       "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
-                       : "memory");
-        }
+      for (int q = 0; q < 8; ++q) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 0]), sl2, -mb));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 1]), sl2, -mb));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 2]), sl2, -mb));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 3]), sl2, -mb));
+        const float p4 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 4]), sl2, -mb));
+        const float p5 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 5]), sl2, -mb));
+        const float p6 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 6]), sl2, -mb));
+        const float p7 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 7]), sl2, -mb));
+        s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
+        const uint32_t chunk = (uint32_t)q ^ (uint32_t)(row & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(T::pack(p0, p1)),
+                     "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
+                     : "memory");
       }
-      l_run += sum;
+      l_run += (s0 + s1) + (s2 + s3);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(i & 1));
     }
-    // ---- epilogue: O / l -> out[b, q, h*dv + j]
+    // ---- epilogue: O / l -> out[b, q, h*dv + j]; the row sum is the sum of the two halves' partial sums
+    {
+      float* xb = xch + (nblk & 1) * 256;
+      xb[half * 128 + row] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l_run += xb[(half ^ 1) * 128 + row];
+    }
     mbar_wait(pv_done((nblk - 1) & 1), (uint32_t)(((nblk - 1) >> 1) & 1));
     tc_fence_after();
     const int q = q0 + row;
     const float inv_l = 1.f / l_run;
     const int b = bh / a.H, h = bh - b * a.H;
     TT* orow = reinterpret_cast<TT*>(a.out) + ((size_t)b * a.Nq + q) * a.ldo + a.out_col0 + h * a.dv;
-    for (int c = 0; c * 32 < a.dv; ++c) {
+    for (int c = half * a.dv_slabs; c < (half + 1) * a.dv_slabs; ++c) {
+      if (c * 32 >= a.dv) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + TM_O + lane_base + c * 32, r);
       tc_wait_ld();
@@ -297,7 +319,7 @@ int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   const int budget = (224 * 1024 - 2048) / SLAB_BYTES;  // slabs that fit beside barriers + alignment slack
   a.num_slots = std::min(10, budget - 4 - q_slabs);
   if (a.num_slots < 2) { set_last_error(__FILE__, __LINE__, "attention: smem"); return -1; }
-  const size_t smem = (size_t)(q_slabs + a.num_slots + 4) * SLAB_BYTES + 8 * (2 * a.num_slots + 7) + 16 + 1024;
+  const size_t smem = (size_t)(q_slabs + a.num_slots + 4) * SLAB_BYTES + 8 * (2 * a.num_slots + 7) + 16 + 2048 + 1024;
   auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
   if (attention_init() != 0) return -1;
   dim3 grid((a.Nq + 127) / 128, a.B * a.H);

@@ -12,6 +12,7 @@ struct alignas(64) AttnArgs {
   int dqk_slabs;    // dqk_pad / 64  (1..8)
   int dv_slabs;     // dv_pad / 64   (1..4)
   int dv;           // valid value columns per head that are stored (multiple of 8)
+  int dqk;          // valid q/k columns (<= dqk_slabs * 64); columns beyond are zero padding
   int q_resident;   // set by the launcher
   int num_slots;    // set by the launcher
   float scale_log2; // softmax scale * log2(e)

@@ -48,6 +48,7 @@ int sdxe_attention(const void* q, const void* k, const void* v, void* out, int B
     a.dqk_slabs = Dpad / 64;
     a.dv_slabs = dvpad / 64;
     a.dv = dv;
+    a.dqk = D;
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = out;
     a.ldo = H * D;

@@ -181,11 +181,12 @@ struct OpRec {
   OpFn fn;
   int kind = K_OTHER;
   double flops = 0, bytes = 0;  // algorithmic work of this launch
+  std::string desc;
   OpRec() {}
   template <class F>
   OpRec(F f) : fn(std::move(f)) {}  // implicit: un-annotated ops are K_OTHER
   template <class F>
-  OpRec(F f, int k, double fl, double by) : fn(std::move(f)), kind(k), flops(fl), bytes(by) {}
+  OpRec(F f, int k, double fl, double by, std::string d = std::string()) : fn(std::move(f)), kind(k), flops(fl), bytes(by), desc(std::move(d)) {}
 };
 
 struct Plan {
@@ -261,8 +262,11 @@ struct Builder {
     const bool b = bf16;
     const double nout = (o.epi == EPI_GEGLU) ? W.N / 2.0 : (double)W.N;
     const double by = 2.0 * ((double)M * W.K + (double)W.N * W.K + (double)M * nout + (o.residual ? (double)M * nout : 0.0));
+    char d[160];
+    snprintf(d, sizeof(d), "gemm M=%lld N=%d K=%d BN=%d st=%d epi=%d res=%d rv=%d dual=%d", (long long)M, W.N, W.K, a.BN, a.num_stages, o.epi,
+             o.residual ? 1 : 0, o.rowvec ? 1 : 0, o.A2 ? 1 : 0);
     ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); }, K_GEMM,
-                         2.0 * (double)M * W.N * W.K, by));
+                         2.0 * (double)M * W.N * W.K, by, d));
     return 0;
   }
 
@@ -287,8 +291,11 @@ struct Builder {
       const bool b = bf16;
       const double Md = (double)a.M;
       const double by = 2.0 * (Md * x.c + (double)W.N * a.K + Md * W.N + (o.residual ? Md * W.N : 0.0));
+      char d[160];
+      snprintf(d, sizeof(d), "conv3 M=%d N=%d Cin=%d HxW=%dx%d BN=%d st=%d res=%d rv=%d", a.M, W.N, x.c, x.h, x.w, a.BN, a.num_stages,
+               o.residual ? 1 : 0, o.rowvec ? 1 : 0);
       ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); }, K_CONV,
-                           2.0 * Md * W.N * a.K, by));
+                           2.0 * Md * W.N * a.K, by, d));
       return 0;
     }
     // generic geometry: explicit im2col (still CUDA; used for odd resolutions / narrow channel counts)
@@ -324,7 +331,7 @@ struct Builder {
     const bool b = bf16;
     if (nw.C != c1 + c2) EFAIL("group_norm: channel mismatch");
     ops->push_back(OpRec([=](cudaStream_t s) { return group_norm_launch(p1, c1, p2, c2, g, bt, po, sp, n, hw, 32, eps, silu, b, s); },
-                         K_GNORM, 0.0, 4.0 * (double)n * hw * (c1 + c2)));
+                         K_GNORM, 0.0, 4.0 * (double)n * hw * (c1 + c2), "gn n=" + std::to_string(n) + " hw=" + std::to_string(hw) + " C=" + std::to_string(c1 + c2)));
     e->release(st);
     return 0;
   }
@@ -333,7 +340,7 @@ struct Builder {
     const int C = nw.C;
     const bool b = bf16;
     ops->push_back(OpRec([=](cudaStream_t s) { return layer_norm_launch(x, g, bt, out, (int)rows, C, 1e-5f, b, s); }, K_LNORM, 0.0,
-                         4.0 * (double)rows * C));
+                         4.0 * (double)rows * C, "ln rows=" + std::to_string(rows) + " C=" + std::to_string(C)));
     return 0;
   }
   int attention(const void* q, const void* k, const void* v, int B, int H, int Nq, int Nk, int d, int dpad, int ldq,
@@ -351,12 +358,15 @@ struct Builder {
       a.dqk_slabs = dpad / 64;
       a.dv_slabs = dvpad / 64;
       a.dv = dv_total > 256 ? dv : d;
+      a.dqk = d;
       a.scale_log2 = scale * 1.4426950408889634f;
       a.out = out; a.ldo = ldo; a.out_col0 = v0;
       const bool b = bf16;
       const double fl = 2.0 * (double)B * H * Nq * Nk * ((double)d + dv);
       const double by = 2.0 * (double)B * H * ((double)Nq * d + (double)Nk * (d + dv) + (double)Nq * dv);
-      ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return attention_launch(a, b, s); }, K_ATTN, fl, by));
+      char dsc[160];
+      snprintf(dsc, sizeof(dsc), "attn B=%d H=%d Nq=%d Nk=%d d=%d dpad=%d dv=%d", B, H, Nq, Nk, d, dpad, dv);
+      ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return attention_launch(a, b, s); }, K_ATTN, fl, by, dsc));
     }
     return 0;
   }
@@ -875,15 +885,19 @@ int run_ops_profiled(sdxe_engine* e, std::vector<OpRec>& ops, cudaStream_t s) {
   }
   cudaStreamSynchronize(s);
   if (rc == 0) {
+    const char* dump = getenv("SDXE_PROFILE_DUMP");
+    FILE* df = dump ? fopen(dump, "a") : nullptr;
     for (size_t i = 0; i < n; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      if (df) fprintf(df, "%zu,%d,%s,%.4f,%.0f,%.0f\n", i, ops[i].kind, ops[i].desc.c_str(), ms * 1000.0, ops[i].flops, ops[i].bytes);
       const int k = ops[i].kind;
       e->prof_ms[k] += ms;
       e->prof_flops[k] += ops[i].flops;
       e->prof_bytes[k] += ops[i].bytes;
       e->prof_launches[k] += 1;
     }
+    if (df) fclose(df);
   }
   for (auto& x : ev) cudaEventDestroy(x);
   return rc;

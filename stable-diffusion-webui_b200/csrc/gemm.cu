@@ -18,6 +18,7 @@
 #include "gemm.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace sdxe {
 
@@ -26,8 +27,7 @@ static constexpr int BLOCK_K = 64;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int TMEM_COLS = 512;
-static constexpr int STAGE_PITCH = 80;                        // 64 B of data + 16 B pad: conflict-free 16-byte row writes
-static constexpr int STAGE_BUF_BYTES = BLOCK_M * STAGE_PITCH;  // 10 KB, double buffered
+static constexpr int SBIAS_BYTES = 2 * 256 * 4;  // per-tile bias slice in smem, double buffered
 
 template <bool BF16>
 struct Epi {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + 8 * (2 * S + 4));
-  uint8_t* stage_base = smem + S * stage_bytes + 8 * (2 * S + 4) + 16;  // 16-byte aligned
+  float* sbias = reinterpret_cast<float*>(smem + S * stage_bytes + 8 * (2 * S + 4) + 16);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,108 +182,111 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Two phases per 32-column chunk of the accumulator tile:
-    //  1. row-per-thread (the only way tcgen05.ld hands out data): TMEM -> regs, + bias (+ per-sample vector, GEGLU),
-    //     pack to 16 bit, write the thread's 64-byte row piece into a padded smem staging buffer;
-    //  2. re-read the staging buffer with a coalescing map (4 consecutive threads own one 64-byte row piece), add the
-    //     residual (read coalesced too; the sum is rounded once more, exactly as the reference's fp16 `x + h`), store.
-    // The staging buffer is double buffered so one named barrier per chunk suffices.
+    // Row-per-thread (the only way tcgen05.ld hands out data). The epilogue is latency-, not issue-bound, so every
+    // global read it needs is taken off the critical path: the tile's bias goes to shared memory once per tile, and
+    // the residual row piece of chunk c+1 is prefetched into registers while chunk c is being converted and stored.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
+    uint32_t tile_ctr = 0;
     const bool geglu = a.epi == EPI_GEGLU;
     const int Nst = geglu ? (a.N / 2) : ((a.N + 7) & ~7);
-    const int out_cols = geglu ? (BN >> 1) : BN;   // output columns produced per tile
+    const int out_cols = geglu ? (BN >> 1) : BN;  // output columns produced per tile
     const int C_heads = a.heads * a.head_dim;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const TT* resid = reinterpret_cast<const TT*>(a.residual);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int m = m_blk * BLOCK_M + row;
       const bool row_ok = m < a.M;
+      const int n_out0 = n_blk * out_cols;  // first output column of this tile
+      float* sb = sbias + (tile_ctr & 1u) * 256;
+      if (a.bias) {
+        for (int j = et; j < BN; j += 128) sb[j] = (n_blk * BN + j < a.N) ? __ldg(a.bias + n_blk * BN + j) : 0.f;
+      }
+      // residual prefetch for the first chunk (before waiting for the accumulator)
+      uint4 res_cur[4], res_nxt[4];
+      const bool has_res = resid != nullptr && row_ok;
+      auto prefetch = [&](int c0, uint4* dst) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n_out0 + c0 + g * 8;
+          if (has_res && c0 + g * 8 < out_cols && n + 8 <= Nst)
+            dst[g] = *reinterpret_cast<const uint4*>(resid + (size_t)m * a.ldr + n);
+          else
+            dst[g] = make_uint4(0, 0, 0, 0);
+        }
+      };
+      prefetch(0, res_cur);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias of this tile visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
       if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv;
-      const int n_out0 = n_blk * out_cols;  // first output column of this tile
 
-      for (int c0 = 0; c0 < out_cols; c0 += 32, ++chunk_ctr) {
+      for (int c0 = 0; c0 < out_cols; c0 += 32) {
         const int nc = min(32, out_cols - c0);
-        uint8_t* stage = stage_base + (chunk_ctr & 1u) * STAGE_BUF_BYTES;
-        // ---- phase 1
         uint32_t r[32];
-        float v[32];
         if (nc == 32) tmem_ld32(t_row + c0, r);
         else tmem_ld16(t_row + c0, r);
+        uint32_t rg[32];
         if (geglu) {
-          uint32_t rg[32];
           const int half = BN >> 1;
           if (nc == 32) tmem_ld32(t_row + half + c0, rg);
           else tmem_ld16(t_row + half + c0, rg);
-          tc_wait_ld();
+        }
+        if (c0 + 32 < out_cols) prefetch(c0 + 32, res_nxt);
+        tc_wait_ld();
 #pragma unroll
-          for (int g = 0; g < 32; g += 8) {
-            if (g < nc) {
+        for (int g = 0; g < 32; g += 8) {
+          if (g < nc) {
+            const int n = n_out0 + c0 + g;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
+            if (geglu) {
+              const int half = BN >> 1;
               float gt[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { v[g + j] = __uint_as_float(r[g + j]); gt[j] = __uint_as_float(rg[g + j]); }
+              for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(rg[g + j]);
               if (a.bias) {
-                E::add_bias8(v + g, a.bias, n_blk * BN + c0 + g, a.N);
-                E::add_bias8(gt, a.bias, n_blk * BN + half + c0 + g, a.N);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] += sb[c0 + g + j]; gt[j] += sb[half + c0 + g + j]; }
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[g + j] *= gelu_erf_f(gt[j]);
-            }
-          }
-        } else {
-          tc_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 32; g += 8) {
-            if (g < nc) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g + j] = __uint_as_float(r[g + j]);
-              const int n = n_out0 + c0 + g;
-              if (a.bias) E::add_bias8(v + g, a.bias, n, a.N);
-              if (rv) E::add_bias8(v + g, rv, n, a.N);
-            }
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 32; g += 8)
-          if (g < nc) E::store8(stage + row * STAGE_PITCH + g * 2, v + g);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // ---- phase 2: 4 threads per row piece (16 B each), 32 rows per pass
-        const int ppr = nc >> 3;  // 16-byte pieces per row: 4 or 2
-        for (int pid = et; pid < BLOCK_M * ppr; pid += 128) {
-          const int rr = pid / ppr, pc = pid - rr * ppr;
-          const int mm = m_blk * BLOCK_M + rr;
-          const int n = n_out0 + c0 + pc * 8;
-          if (mm < a.M && n + 8 <= Nst) {
-            uint4 u = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + pc * 16);
-            if (a.epi == EPI_HEADS) {
-              const int which = n / C_heads, cc = n - which * C_heads;
-              const int head = cc / a.head_dim, off = cc - head * a.head_dim;
-              const int b = mm / a.tokens, tok = mm - b * a.tokens;
-              TT* dst = reinterpret_cast<TT*>(a.outs[which]) + ((size_t)(b * a.heads + head) * a.tokens + tok) * a.head_pad + off;
-              *reinterpret_cast<uint4*>(dst) = u;
+              for (int j = 0; j < 8; ++j) v[j] *= gelu_fast_f(gt[j]);
             } else {
-              if (a.residual) {
-                float f[8];
-                float2 t2;
-                t2 = T16<BF16>::unpack(u.x); f[0] = t2.x; f[1] = t2.y;
-                t2 = T16<BF16>::unpack(u.y); f[2] = t2.x; f[3] = t2.y;
-                t2 = T16<BF16>::unpack(u.z); f[4] = t2.x; f[5] = t2.y;
-                t2 = T16<BF16>::unpack(u.w); f[6] = t2.x; f[7] = t2.y;
-                E::add_res8(f, reinterpret_cast<const TT*>(a.residual) + (size_t)mm * a.ldr + n);
-                E::store8(reinterpret_cast<TT*>(a.out) + (size_t)mm * a.ldo + n, f);
+              if (a.bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += sb[c0 + g + j];
+              }
+              if (rv) E::add_bias8(v, rv, n, a.N);
+            }
+            if (row_ok && n + 8 <= Nst) {
+              if (a.epi == EPI_HEADS) {  // column n -> (which tensor, head, offset); row m -> (batch, token)
+                const int which = n / C_heads, cc = n - which * C_heads;
+                const int head = cc / a.head_dim, off = cc - head * a.head_dim;
+                const int b = m / a.tokens, tok = m - b * a.tokens;
+                TT* dst = reinterpret_cast<TT*>(a.outs[which]) + ((size_t)(b * a.heads + head) * a.tokens + tok) * a.head_pad + off;
+                E::store8(dst, v);
               } else {
-                *reinterpret_cast<uint4*>(reinterpret_cast<TT*>(a.out) + (size_t)mm * a.ldo + n) = u;
+                if (has_res) {
+                  float2 f;
+                  const uint4 u = res_cur[g >> 3];
+                  f = T16<BF16>::unpack(u.x); v[0] += f.x; v[1] += f.y;
+                  f = T16<BF16>::unpack(u.y); v[2] += f.x; v[3] += f.y;
+                  f = T16<BF16>::unpack(u.z); v[4] += f.x; v[5] += f.y;
+                  f = T16<BF16>::unpack(u.w); v[6] += f.x; v[7] += f.y;
+                }
+                E::store8(reinterpret_cast<TT*>(a.out) + (size_t)m * a.ldo + n, v);
               }
             }
           }
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
       }
       tc_fence_before();
       __syncwarp();
@@ -321,7 +324,7 @@ bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn) {
 
 int gemm_pick_stages(int BN) {
   const int stage_bytes = A_STAGE_BYTES + BN * 128;
-  int s = (227 * 1024 - 2048 - 2 * STAGE_BUF_BYTES) / stage_bytes;
+  int s = (227 * 1024 - 2048 - SBIAS_BYTES) / stage_bytes;
   return std::max(2, std::min(s, 8));
 }
 
@@ -359,7 +362,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
   const int stage_bytes = A_STAGE_BYTES + a.BN * 128;
-  const size_t smem = (size_t)a.num_stages * stage_bytes + 8 * (2 * a.num_stages + 4) + 16 + 2 * STAGE_BUF_BYTES + 1024;
+  const size_t smem = (size_t)a.num_stages * stage_bytes + 8 * (2 * a.num_stages + 4) + 16 + SBIAS_BYTES + 1024;
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
   const int tiles = num_m * num_n;
   if (tiles <= 0) return 0;

@@ -24,6 +24,7 @@ struct alignas(64) GemmArgs {
   int bh, bn;
   int epi;
   int ldrv;          // row pitch (elements) of rowvec
+  int reserved0;
   const float* bias;    // [N] (EPI_GEGLU: interleaved like the weights) or null
   const float* rowvec;  // [M / rows_per_sample, N] per-sample vector added to every row of the sample, or null
   int rows_per_sample;

@@ -65,9 +65,12 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   const int c = vec * 8;
+  const uint4* src = (c < c1) ? x1 : x2;
+  const int cs = (c < c1) ? c1 : c2, co = (c < c1) ? c : c - c1;
+#pragma unroll 4
   for (int p = p0 + prow; p < p1; p += rpi) {
     const size_t pix = (size_t)n * hw + p;
-    const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
+    const uint4 u = __ldg(src + (pix * cs + co) / 8);
     float v[8];
     unpack8<BF16>(u, v);
 #pragma unroll
@@ -117,17 +120,22 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint
     const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
     float v[8];
     unpack8<BF16>(u, v);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c)), bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
     int g_prev = -1;
     float mean = 0.f, rstd = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cpg;
       if (g != g_prev) {
-        mean = __ldg(stats + ((size_t)n * groups + g) * 2);
-        rstd = __ldg(stats + ((size_t)n * groups + g) * 2 + 1);
+        const float2 mr = __ldg(reinterpret_cast<const float2*>(stats + ((size_t)n * groups + g) * 2));
+        mean = mr.x;
+        rstd = mr.y;
         g_prev = g;
       }
-      float y = (v[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      float y = (v[j] - mean) * rstd * gm[j] + bt[j];
       if (SILU) y = silu_f(y);
       v[j] = y;
     }
@@ -191,43 +199,56 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
 template <bool BF16>
 __global__ void layer_norm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, uint4* __restrict__ out, int rows, int C, float eps) {
+  constexpr int MAXV = 8;  // up to 8 x 32 x 8 = 2048 channels held in registers (one global read of the row)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int V = C >> 3;
   const uint4* xr = x + (size_t)warp * V;
+  float f[MAXV][8];
   float sum = 0.f;
-  for (int v = lane; v < V; v += 32) {
-    float f[8];
-    unpack8<BF16>(__ldg(xr + v), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum += f[j];
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      unpack8<BF16>(__ldg(xr + v), f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / (float)C;
   float sq = 0.f;
-  for (int v = lane; v < V; v += 32) {
-    float f[8];
-    unpack8<BF16>(__ldg(xr + v), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; sq += d * d; }
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / (float)C + eps);
   uint4* orow = out + (size_t)warp * V;
-  for (int v = lane; v < V; v += 32) {
-    float f[8];
-    unpack8<BF16>(__ldg(xr + v), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
-    orow[v] = pack8<BF16>(f);
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (f[i][j] - mean) * rstd * gm[j] + bt[j];
+      orow[v] = pack8<BF16>(y);
+    }
   }
 }
 
 int layer_norm_launch(const void* x, const float* gamma, const float* beta, void* out, int rows, int c, float eps,
                       bool bf16, cudaStream_t s) {
-  if (c % 8) { set_last_error(__FILE__, __LINE__, "layer_norm: C % 8"); return -1; }
+  if (c % 8 || c > 2048) { set_last_error(__FILE__, __LINE__, "layer_norm: C % 8 != 0 or C > 2048"); return -1; }
   const int blocks = (rows + 3) / 4;
   if (bf16) layer_norm_kernel<true><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
   else layer_norm_kernel<false><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
