@@ -936,16 +936,18 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
     const LinW te0 = e->te0, te2 = e->te2, le0 = e->le0, le2 = e->le2, ea = e->emb_all;
     float *pt = (float*)temb.p, *p1 = (float*)e1.p, *pe = (float*)emb.p, *pl = (float*)l1.p, *pa = (float*)emb_all.p, *py = (float*)y32.p;
     const int adm = cfg.adm_in_channels, etot = e->emb_total;
-    B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pt, mc, te0.w, te0.b, nullptr, p1, ted, n, ted, mc, false, bf16, s); });
+    // time_embed = Linear -> SiLU -> Linear; every consumer of `emb` (the ResBlocks' emb_layers) applies SiLU first,
+    // so the SiLU'd vector is what gets stored (rounded through the 16-bit type at each step like the reference).
+    B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pt, mc, te0.w, te0.b, nullptr, p1, ted, n, ted, mc, true, bf16, s); });
     if (adm > 0) {
-      // emb = time_embed(t_emb) + label_emb(y): compute label branch first, add inside the last time_embed GEMM
-      B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(py, adm, le0.w, le0.b, nullptr, pl, ted, n, ted, adm, false, bf16, s); });
-      B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pl, ted, le2.w, le2.b, nullptr, pe, ted, n, ted, ted, true, bf16, s); });
+      // emb = time_embed(t_emb) + label_emb(y): label branch first, the sum happens inside the last time_embed GEMM
+      B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(py, adm, le0.w, le0.b, nullptr, pl, ted, n, ted, adm, true, bf16, s); });
+      B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pl, ted, le2.w, le2.b, nullptr, pe, ted, n, ted, ted, false, bf16, s); });
       B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(p1, ted, te2.w, te2.b, pe, pe, ted, n, ted, ted, true, bf16, s); });
     } else {
       B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(p1, ted, te2.w, te2.b, nullptr, pe, ted, n, ted, ted, true, bf16, s); });
     }
-    B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pe, ted, ea.w, ea.b, nullptr, pa, etot, n, etot, ted, true, bf16, s); });
+    B.ops->push_back([=](cudaStream_t s) { return skinny_linear_launch(pe, ted, ea.w, ea.b, nullptr, pa, etot, n, etot, ted, false, bf16, s); });
   }
   const float* emb_ptr = (const float*)emb_all.p;
   const int ld_emb = e->emb_total;

@@ -13,8 +13,9 @@
 //              4D NHWC box (64 ch x W x bh x bn) fetched at the tap's (dx-1, dy-1) offset: TMA's out-of-bounds
 //              zero fill IS the convolution padding, so no im2col buffer ever exists.
 //   warp 1   : tcgen05.mma issuer (single thread), fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-5: epilogue. tcgen05.ld the accumulator (thread = row), fuse bias / timestep-embedding vector /
-//              residual / GEGLU, convert to 16 bit, store.
+//   warps 2-9: epilogue (two warps per TMEM lane quarter, alternating 32-column chunks). tcgen05.ld the accumulator
+//              (thread = row), fuse bias / timestep-embedding vector / residual / GEGLU, convert to 16 bit, store.
+//              Latency-bound, so: bias staged in smem per tile, residual prefetched one chunk ahead.
 #include "gemm.cuh"
 #include <algorithm>
 #include <cstdio>
@@ -25,7 +26,7 @@ namespace sdxe {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 static constexpr int TMEM_COLS = 512;
 static constexpr int SBIAS_BYTES = 2 * 256 * 4;  // per-tile bias slice in smem, double buffered
 
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&a.tmA);
@@ -185,9 +186,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     // Row-per-thread (the only way tcgen05.ld hands out data). The epilogue is latency-, not issue-bound, so every
     // global read it needs is taken off the critical path: the tile's bias goes to shared memory once per tile, and
     // the residual row piece of chunk c+1 is prefetched into registers while chunk c is being converted and stored.
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warps w and w+4 share it)
+    const int ehalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
     const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;     // 0..255 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t tile_ctr = 0;
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       const int n_out0 = n_blk * out_cols;  // first output column of this tile
       float* sb = sbias + (tile_ctr & 1u) * 256;
       if (a.bias) {
-        for (int j = et; j < BN; j += 128) sb[j] = (n_blk * BN + j < a.N) ? __ldg(a.bias + n_blk * BN + j) : 0.f;
+        for (int j = et; j < BN; j += 256) sb[j] = (n_blk * BN + j < a.N) ? __ldg(a.bias + n_blk * BN + j) : 0.f;
       }
       // residual prefetch for the first chunk (before waiting for the accumulator)
       uint4 res_cur[4], res_nxt[4];
@@ -218,15 +220,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             dst[g] = make_uint4(0, 0, 0, 0);
         }
       };
-      prefetch(0, res_cur);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias of this tile visible to all epilogue warps
+      prefetch(ehalf * 32, res_cur);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
       if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv;
 
-      for (int c0 = 0; c0 < out_cols; c0 += 32) {
+      for (int c0 = ehalf * 32; c0 < out_cols; c0 += 64) {
         const int nc = min(32, out_cols - c0);
         uint32_t r[32];
         if (nc == 32) tmem_ld32(t_row + c0, r);
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           if (nc == 32) tmem_ld32(t_row + half + c0, rg);
           else tmem_ld16(t_row + half + c0, rg);
         }
-        if (c0 + 32 < out_cols) prefetch(c0 + 32, res_nxt);
+        if (c0 + 64 < out_cols) prefetch(c0 + 64, res_nxt);
         tc_wait_ld();
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {

@@ -435,7 +435,7 @@ int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int
 template <bool BF16, int MT, int NPW>
 __global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, const uint4* __restrict__ W,
                                      const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ out,
-                                     int ldo, int M, int N, int K, int silu_in) {
+                                     int ldo, int M, int N, int K, int silu_out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n0 = warp * NPW;
   if (n0 >= N) return;
@@ -461,11 +461,7 @@ __global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, cons
         if (m0 + r < M) {
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8));
           const float4 a1 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8 + 4));
-          float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          if (silu_in) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = round16<BF16>(silu_f(a[j]));
-          }
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
           for (int i = 0; i < NPW; ++i)
 #pragma unroll
@@ -483,6 +479,7 @@ __global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, cons
         if (lane == 0 && n0 + i < N && m0 + r < M) {
           v = round16<BF16>(v + (b ? __ldg(b + n0 + i) : 0.f));
           if (add) v = round16<BF16>(v + add[(size_t)(m0 + r) * ldo + n0 + i]);
+          if (silu_out) v = round16<BF16>(silu_f(v));  // the only consumer applies SiLU first (emb_layers / time_embed)
           out[(size_t)(m0 + r) * ldo + n0 + i] = v;
         }
       }
@@ -490,15 +487,15 @@ __global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, cons
 }
 
 int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
-                         int M, int N, int K, bool silu_in, bool bf16, cudaStream_t s) {
+                         int M, int N, int K, bool silu_out, bool bf16, cudaStream_t s) {
   if (K % 8 || ldi % 4) { set_last_error(__FILE__, __LINE__, "skinny_linear: K % 8"); return -1; }
-  constexpr int MT = 8, NPW = 2;
+  constexpr int MT = 16, NPW = 2;
   const int warps = (N + NPW - 1) / NPW;
   const int blocks = (warps + 3) / 4;
   if (bf16)
-    skinny_linear_kernel<true, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_in ? 1 : 0);
+    skinny_linear_kernel<true, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0);
   else
-    skinny_linear_kernel<false, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_in ? 1 : 0);
+    skinny_linear_kernel<false, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0);
   SDXE_LAUNCH_CHECK();
   return 0;
 }

@@ -33,9 +33,9 @@ int pad_heads_launch(const void* src, void* dst, int64_t rows, int D, int Dpad, 
 // ---- embeddings --------------------------------------------------------------------------------------------
 // modules/sd_hijack_unet.py:58-78: emb[m, :] = [cos(t*f) , sin(t*f)], rounded through the 16-bit type; fp32 out.
 int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int dim, bool bf16, cudaStream_t s);
-// out[m, n] = round16(sum_k act(in[m,k]) * W[n,k] + b[n]) (+ add[m,n]); in/out fp32 [M<=64, *]; W 16-bit [N,K]
+// out[m, n] = act(round16(sum_k in[m,k] * W[n,k] + b[n]) (+ add[m,n])), act = SiLU (rounded) if silu_out; in/out fp32; W 16-bit [N,K]
 int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
-                         int M, int N, int K, bool silu_in, bool bf16, cudaStream_t s);
+                         int M, int N, int K, bool silu_out, bool bf16, cudaStream_t s);
 int cast_to_f32_launch(const void* src, int src_dtype, float* dst, int64_t n, bool round16, bool bf16, cudaStream_t s);
 
 // ---- weight repack (run once at finalize) -------------------------------------------------------------------
