@@ -21,6 +21,7 @@
 //               max moved by more than 2^8); final 1/l scaling and store.
 #include "attention.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace sdxe {
 
@@ -303,6 +304,7 @@ int attention_init() {
   if (!done) {
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (attention2_init() != 0) return -1;
     done = true;
   }
   return 0;
@@ -310,6 +312,11 @@ int attention_init() {
 
 int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   AttnArgs a = a_in;
+  {
+    static int use2 = -1;
+    if (use2 < 0) { const char* e = getenv("SDXE_ATTN2"); use2 = e ? atoi(e) : 1; }
+    if (use2 && attention2_eligible(a)) return attention2_launch(a, bf16, stream);
+  }
   if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {
     set_last_error(__FILE__, __LINE__, "attention: unsupported head size");
     return -1;

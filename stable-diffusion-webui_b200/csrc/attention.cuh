@@ -23,5 +23,9 @@ struct alignas(64) AttnArgs {
 
 int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
 int attention_init();
+// two-query-tile variant (attention2.cu), used automatically by attention_launch when eligible
+bool attention2_eligible(const AttnArgs& a);
+int attention2_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
+int attention2_init();
 
 }  // namespace sdxe

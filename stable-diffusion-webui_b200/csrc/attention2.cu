@@ -1,0 +1,300 @@
+// Two-query-tile flash attention for sm_100a (head dims up to 128): the variant used for the UNet's large
+// self-attention layers. Same contract as attention.cu (AttnArgs), but one CTA owns 256 query rows (tiles A and B):
+//
+//  * every K / V slab fetched from L2 is used by two S = Q K^T and two O += P V tile products, which halves the
+//    L2 -> shared-memory traffic per FLOP. With small head dims (SD1.5: d = 40) a 128-row tile is L2-bound at
+//    ~80 FLOP/byte; this kernel doubles that.
+//  * the two tiles ping-pong on the tensor pipe: while tile A's rows are in their softmax, the MMA thread issues tile
+//    B's S and PV, and vice versa (the FA-4 schedule). Warps 2-5 are tile A's softmax (one thread per row), warps
+//    6-9 tile B's, so every scheduler interleaves two softmax warps.
+//  * TMEM: S_A | S_B | O_A | O_B at columns 0 / 128 / 256 / 384 (fp32, 128 columns each).
+//
+// Barrier protocol (all single-phase-per-iteration, parity = i & 1):
+//   s_full[T]   MMA -> softmax_T : S_T(i) complete in TMEM
+//   p_ready[T]  softmax_T -> MMA : P_T(i) in smem, S_T(i) consumed (so S_T(i+1) may overwrite it)
+//   pv_done[T]  MMA -> softmax_T : O_T holds blocks <= i, P_T buffer free
+#include "attention.cuh"
+#include <algorithm>
+
+namespace sdxe {
+
+static constexpr int SLAB2 = 16384;
+static constexpr int ATT2_THREADS = 320;
+
+template <bool BF16>
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnArgs a) {
+  using T = T16<BF16>;
+  using TT = typename T::type;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sbase = raw + pad;
+
+  const int NS = a.num_slots;
+  const int QS = a.dqk_slabs, VS = a.dv_slabs;
+  const uint32_t sQ = sbase;                          // [2 tiles][QS] slabs
+  const uint32_t sRing = sQ + 2 * QS * SLAB2;
+  const uint32_t sP = sRing + NS * SLAB2;             // [2 tiles][2 slabs]
+  const uint32_t bar_base = sP + 4 * SLAB2;
+  auto slot_full = [&](int s) { return bar_base + 8u * s; };
+  auto slot_empty = [&](int s) { return bar_base + 8u * (NS + s); };
+  const uint32_t q_full = bar_base + 8u * (2 * NS);
+  auto s_full = [&](int t) { return bar_base + 8u * (2 * NS + 1 + t); };
+  auto p_ready = [&](int t) { return bar_base + 8u * (2 * NS + 3 + t); };
+  auto pv_done = [&](int t) { return bar_base + 8u * (2 * NS + 5 + t); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int bh = blockIdx.y;
+  const int nblk = (a.Nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
+    mbar_init(q_full, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_ready(t), 4); mbar_init(pv_done(t), 1); }
+    fence_mbar_init();
+    tma_prefetch_desc(&a.tmQ);
+    tma_prefetch_desc(&a.tmK);
+    tma_prefetch_desc(&a.tmV);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * QS * SLAB2);
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < QS; ++c) tma_load_3d(sQ + (t * QS + c) * SLAB2, &a.tmQ, q_full, c * 64, q0 + t * 128, bh);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto push = [&](const CUtensorMap* tm, int c0, int r0) {
+        mbar_wait(slot_empty(slot), phase ^ 1u);
+        mbar_expect_tx(slot_full(slot), SLAB2);
+        tma_load_3d(sRing + slot * SLAB2, tm, slot_full(slot), c0, r0, bh);
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+      };
+      // ring order == consumption order: K_0, (K_1, V_0), (K_2, V_1), ..., V_{n-1}
+      for (int i = 0; i <= nblk; ++i) {
+        if (i < nblk)
+          for (int c = 0; c < QS; ++c) push(&a.tmK, c * 64, i * 128);
+        if (i >= 1)
+          for (int vs = 0; vs < VS; ++vs) push(&a.tmV, vs * 64, (i - 1) * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, 128, 128, 0, 0);
+      const uint32_t idesc_pv = umma_idesc(BF16 ? 1 : 0, 128, 64, 0, 1);
+      const int ksteps_last = (a.dqk - (QS - 1) * 64 + 15) / 16;
+      const int n_last = (a.dv - (VS - 1) * 64 + 15) / 16 * 16;
+      const uint32_t idesc_pv_last = umma_idesc(BF16 ? 1 : 0, 128, n_last, 0, 1);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto pop = [&](int& slot_id) -> uint32_t {  // wait for the next slab in ring order; caller releases it later
+        mbar_wait(slot_full(slot), phase);
+        slot_id = slot;
+        const uint32_t addr = sRing + slot * SLAB2;
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+        return addr;
+      };
+      auto issue_s = [&](int t, const uint32_t* k_addr) {
+        const uint32_t d_s = tmem_base + (uint32_t)(t * 128);
+        for (int c = 0; c < QS; ++c) {
+          const uint64_t qd = umma_desc_sw128(sQ + (t * QS + c) * SLAB2, 16, 1024);
+          const uint64_t kd = umma_desc_sw128(k_addr[c], 16, 1024);
+          const int ks = (c == QS - 1) ? ksteps_last : 4;
+          for (int k = 0; k < ks; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full(t));
+      };
+      auto issue_pv = [&](int t, const uint32_t* v_addr, int j) {
+        const uint32_t sPt = sP + (uint32_t)t * 2 * SLAB2;
+        for (int vs = 0; vs < VS; ++vs) {
+          const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t pd = umma_desc_sw128(sPt + (k >> 2) * SLAB2, 16, 1024) + 2 * (k & 3);
+            const uint64_t vd = umma_desc_sw128(v_addr[vs] + k * 2048, SLAB2, 1024);
+            tc_mma_f16(d_o, pd, vd, (vs == VS - 1) ? idesc_pv_last : idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(pv_done(t));
+      };
+      uint32_t k_addr[2], v_addr[2];
+      int k_slot[2], v_slot[2];
+      mbar_wait(q_full, 0);
+      for (int c = 0; c < QS; ++c) k_addr[c] = pop(k_slot[c]);
+      tc_fence_after();
+      issue_s(0, k_addr);
+      issue_s(1, k_addr);
+      for (int c = 0; c < QS; ++c) tc_commit(slot_empty(k_slot[c]));
+      for (int i = 0; i < nblk; ++i) {
+        const bool more = i + 1 < nblk;
+        if (more)
+          for (int c = 0; c < QS; ++c) k_addr[c] = pop(k_slot[c]);
+        for (int vs = 0; vs < VS; ++vs) v_addr[vs] = pop(v_slot[vs]);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(p_ready(t), (uint32_t)(i & 1));
+          tc_fence_after();
+          if (more) issue_s(t, k_addr);
+          issue_pv(t, v_addr, i);
+        }
+        if (more)
+          for (int c = 0; c < QS; ++c) tc_commit(slot_empty(k_slot[c]));
+        for (int vs = 0; vs < VS; ++vs) tc_commit(slot_empty(v_slot[vs]));
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / epilogue (one thread per row)
+    const int quarter = warp & 3;
+    const int t = (warp - 2) >> 2;  // tile
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + (uint32_t)(t * 128) + lane_base;
+    const uint32_t t_o = tmem_base + 256u + (uint32_t)(t * 128) + lane_base;
+    const uint32_t p_row = sP + (uint32_t)t * 2 * SLAB2 + row * 128;
+    const float sl2 = a.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int i = 0; i < nblk; ++i) {
+      mbar_wait(s_full(t), (uint32_t)(i & 1));
+      tc_fence_after();
+      const int kv0 = i * 128;
+      uint32_t sreg[128];
+      tmem_ld32(t_s, sreg);
+      tmem_ld32(t_s + 32, sreg + 32);
+      tmem_ld32(t_s + 64, sreg + 64);
+      tmem_ld32(t_s + 96, sreg + 96);
+      tc_wait_ld();
+      if (kv0 + 128 > a.Nk) {
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
+          if (kv0 + j >= a.Nk) sreg[j] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 128; j += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sreg[j]));
+        mx1 = fmaxf(mx1, __uint_as_float(sreg[j + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sreg[j + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sreg[j + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_cand = fmaxf(m_run, mx);
+      const bool need = (m_cand - m_run) * sl2 > 8.f;  // lazy rescale (first block: +inf > 8)
+      if (i >= 1) {
+        mbar_wait(pv_done(t), (uint32_t)((i - 1) & 1));  // O_T holds blocks < i, P_T buffer free
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = ex2_approx((m_run - m_cand) * sl2);
+        if (i >= 1) {
+          for (int c = 0; c < a.dv_slabs * 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_o + c * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+            tmem_st32(t_o + c * 32, r);
+          }
+          tc_wait_st();
+        }
+        l_run *= alpha;
+        m_run = m_cand;
+      }
+      const float mb = m_run * sl2;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 0]), sl2, -mb));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 1]), sl2, -mb));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 2]), sl2, -mb));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 3]), sl2, -mb));
+        const float p4 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 4]), sl2, -mb));
+        const float p5 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 5]), sl2, -mb));
+        const float p6 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 6]), sl2, -mb));
+        const float p7 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 7]), sl2, -mb));
+        s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
+        // P tile = two K-major 128B-swizzle atoms of 64 key columns; 16-byte chunk q of this row
+        const uint32_t chunk = (uint32_t)(q & 7) ^ (uint32_t)(row & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (q >> 3) * SLAB2 + chunk * 16),
+                     "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
+                     : "memory");
+      }
+      l_run += (s0 + s1) + (s2 + s3);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready(t));
+    }
+    // ---- epilogue
+    mbar_wait(pv_done(t), (uint32_t)((nblk - 1) & 1));
+    tc_fence_after();
+    const int q = q0 + t * 128 + row;
+    const float inv_l = 1.f / l_run;
+    const int b = bh / a.H, h = bh - b * a.H;
+    TT* orow = reinterpret_cast<TT*>(a.out) + ((size_t)b * a.Nq + q) * a.ldo + a.out_col0 + h * a.dv;
+    for (int c = 0; c * 32 < a.dv; ++c) {
+      uint32_t r[32];
+      tmem_ld32(t_o + c * 32, r);
+      tc_wait_ld();
+      if (q < a.Nq) {
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+          if (c * 32 + g + 8 <= a.dv) {
+            uint4 u;
+            u.x = T::pack(__uint_as_float(r[g + 0]) * inv_l, __uint_as_float(r[g + 1]) * inv_l);
+            u.y = T::pack(__uint_as_float(r[g + 2]) * inv_l, __uint_as_float(r[g + 3]) * inv_l);
+            u.z = T::pack(__uint_as_float(r[g + 4]) * inv_l, __uint_as_float(r[g + 5]) * inv_l);
+            u.w = T::pack(__uint_as_float(r[g + 6]) * inv_l, __uint_as_float(r[g + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attention2_init() {
+  static bool done = false;
+  if (!done) {
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done = true;
+  }
+  return 0;
+}
+
+bool attention2_eligible(const AttnArgs& a) {
+  return a.dqk_slabs <= 2 && a.dv_slabs <= 2 && a.Nq >= 256 && a.dv <= 128;
+}
+
+int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
+  AttnArgs a = a_in;
+  const int budget = (224 * 1024 - 2048) / SLAB2;  // 13 slabs
+  a.q_resident = 1;
+  a.num_slots = std::min(10, budget - 4 - 2 * a.dqk_slabs);
+  if (a.num_slots < a.dqk_slabs + a.dv_slabs + 1) { set_last_error(__FILE__, __LINE__, "attention2: smem"); return -1; }
+  const size_t smem = (size_t)(2 * a.dqk_slabs + a.num_slots + 4) * SLAB2 + 8 * (2 * a.num_slots + 7) + 16 + 1024;
+  if (attention2_init() != 0) return -1;
+  auto kern = bf16 ? attention2_kernel<true> : attention2_kernel<false>;
+  dim3 grid((a.Nq + 255) / 256, a.B * a.H);
+  kern<<<grid, ATT2_THREADS, smem, stream>>>(a);
+  SDXE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdxe

@@ -235,13 +235,18 @@ SDXE_DEVINL float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-SDXE_DEVINL float silu_f(float x) { return x / (1.f + __expf(-x)); }
+SDXE_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+SDXE_DEVINL float silu_f(float x) { return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 SDXE_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 // erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below 16-bit output resolution):
 // one MUFU.EX2, one MUFU.RCP and a handful of FMAs instead of libdevice erff's branchy ~30 instructions.
 SDXE_DEVINL float gelu_fast_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
