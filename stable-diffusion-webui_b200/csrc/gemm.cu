@@ -65,7 +65,9 @@ struct Epi {
   }
 };
 
-template <bool BF16>
+// EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
+// two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
+template <bool BF16, int EPI, bool RES, bool ROWVEC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
   using E = Epi<BF16>;
   using TT = typename T16<BF16>::type;
@@ -183,9 +185,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Row-per-thread (the only way tcgen05.ld hands out data). The epilogue is latency-, not issue-bound, so every
-    // global read it needs is taken off the critical path: the tile's bias goes to shared memory once per tile, and
-    // the residual row piece of chunk c+1 is prefetched into registers while chunk c is being converted and stored.
+    // Row-per-thread (the only way tcgen05.ld hands out data). Latency-bound, so every global read is taken off the
+    // critical path: the tile's bias goes to shared memory once per tile (zeros when there is none: no branch), the
+    // residual row piece of the next chunk is prefetched into registers while the current chunk is converted and
+    // stored, and full interior chunks take a guard-free, fully unrolled path.
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warps w and w+4 share it)
     const int ehalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
     const int row = quarter * 32 + lane;
@@ -193,31 +196,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t tile_ctr = 0;
-    const bool geglu = a.epi == EPI_GEGLU;
-    const int Nst = geglu ? (a.N / 2) : ((a.N + 7) & ~7);
-    const int out_cols = geglu ? (BN >> 1) : BN;  // output columns produced per tile
+    constexpr bool GEGLU = EPI == EPI_GEGLU;
+    const int Nst = GEGLU ? (a.N / 2) : ((a.N + 7) & ~7);
+    const int out_cols = GEGLU ? (BN >> 1) : BN;  // output columns produced per tile
+    const int half = BN >> 1;
     const int C_heads = a.heads * a.head_dim;
     const TT* resid = reinterpret_cast<const TT*>(a.residual);
+    TT* const outp = reinterpret_cast<TT*>(a.out);
+    const float* const biasp = a.bias;
+    const int M = a.M, N = a.N, ldo = a.ldo, ldr = a.ldr;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int m = m_blk * BLOCK_M + row;
-      const bool row_ok = m < a.M;
+      const bool row_ok = m < M;
       const int n_out0 = n_blk * out_cols;  // first output column of this tile
       float* sb = sbias + (tile_ctr & 1u) * 256;
-      if (a.bias) {
-        for (int j = et; j < BN; j += 256) sb[j] = (n_blk * BN + j < a.N) ? __ldg(a.bias + n_blk * BN + j) : 0.f;
-      }
-      // residual prefetch for the first chunk (before waiting for the accumulator)
+      for (int j = et; j < BN; j += 256) sb[j] = (biasp != nullptr && n_blk * BN + j < N) ? __ldg(biasp + n_blk * BN + j) : 0.f;
       uint4 res_cur[4], res_nxt[4];
-      const bool has_res = resid != nullptr && row_ok;
+      const TT* res_row = RES ? resid + (size_t)m * ldr + n_out0 : nullptr;
       auto prefetch = [&](int c0, uint4* dst) {
+        if (RES) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n_out0 + c0 + g * 8;
-          if (has_res && c0 + g * 8 < out_cols && n + 8 <= Nst)
-            dst[g] = *reinterpret_cast<const uint4*>(resid + (size_t)m * a.ldr + n);
-          else
-            dst[g] = make_uint4(0, 0, 0, 0);
+          for (int g = 0; g < 4; ++g) {
+            const int cc = c0 + g * 8;
+            if (row_ok && cc < out_cols && n_out0 + cc + 8 <= Nst) dst[g] = *reinterpret_cast<const uint4*>(res_row + cc);
+            else dst[g] = make_uint4(0, 0, 0, 0);
+          }
         }
       };
       prefetch(ehalf * 32, res_cur);
@@ -226,55 +230,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
-      if (a.rowvec != nullptr && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv;
+      if (ROWVEC && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv + n_out0;
+      TT* const out_row = outp + (size_t)m * ldo + n_out0;
+      int hb = 0, htok = 0;
+      if (EPI == EPI_HEADS) { hb = m / a.tokens; htok = m - hb * a.tokens; }
+      const bool tile_full = row_ok && (n_out0 + out_cols <= Nst);
 
       for (int c0 = ehalf * 32; c0 < out_cols; c0 += 64) {
         const int nc = min(32, out_cols - c0);
         uint32_t r[32];
+        uint32_t rg[GEGLU ? 32 : 1];
         if (nc == 32) tmem_ld32(t_row + c0, r);
         else tmem_ld16(t_row + c0, r);
-        uint32_t rg[32];
-        if (geglu) {
-          const int half = BN >> 1;
+        if (GEGLU) {
           if (nc == 32) tmem_ld32(t_row + half + c0, rg);
           else tmem_ld16(t_row + half + c0, rg);
         }
         if (c0 + 64 < out_cols) prefetch(c0 + 64, res_nxt);
         tc_wait_ld();
+        // head-scatter bookkeeping advances incrementally (no divisions in the loop)
+        int h_which = 0, h_head = 0, h_off = 0;
+        if (EPI == EPI_HEADS) {
+          const int n = n_out0 + c0;
+          h_which = n / C_heads;
+          const int cc = n - h_which * C_heads;
+          h_head = cc / a.head_dim;
+          h_off = cc - h_head * a.head_dim;
+        }
+        const bool fast = tile_full && nc == 32;
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
-          if (g < nc) {
-            const int n = n_out0 + c0 + g;
+          if (fast || g < nc) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
-            if (geglu) {
-              const int half = BN >> 1;
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + c0 + g + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (GEGLU) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + half + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + half + c0 + g + 4);
               float gt[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(rg[g + j]);
-              if (a.bias) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { v[j] += sb[c0 + g + j]; gt[j] += sb[half + c0 + g + j]; }
-              }
+              for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(rg[(GEGLU ? g : 0) + (GEGLU ? j : 0)]);
+              gt[0] += b0.x; gt[1] += b0.y; gt[2] += b0.z; gt[3] += b0.w;
+              gt[4] += b1.x; gt[5] += b1.y; gt[6] += b1.z; gt[7] += b1.w;
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] *= gelu_fast_f(gt[j]);
-            } else {
-              if (a.bias) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += sb[c0 + g + j];
-              }
-              if (rv) E::add_bias8(v, rv, n, a.N);
             }
-            if (row_ok && n + 8 <= Nst) {
-              if (a.epi == EPI_HEADS) {  // column n -> (which tensor, head, offset); row m -> (batch, token)
-                const int which = n / C_heads, cc = n - which * C_heads;
-                const int head = cc / a.head_dim, off = cc - head * a.head_dim;
-                const int b = m / a.tokens, tok = m - b * a.tokens;
-                TT* dst = reinterpret_cast<TT*>(a.outs[which]) + ((size_t)(b * a.heads + head) * a.tokens + tok) * a.head_pad + off;
+            if (ROWVEC) {
+              if (rv) {
+                if (fast || n_out0 + c0 + g + 8 <= N) {
+                  const float4 e0 = __ldg(reinterpret_cast<const float4*>(rv + c0 + g)), e1 = __ldg(reinterpret_cast<const float4*>(rv + c0 + g + 4));
+                  v[0] += e0.x; v[1] += e0.y; v[2] += e0.z; v[3] += e0.w;
+                  v[4] += e1.x; v[5] += e1.y; v[6] += e1.z; v[7] += e1.w;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (n_out0 + c0 + g + j < N) v[j] += __ldg(rv + c0 + g + j);
+                }
+              }
+            }
+            if (fast || (row_ok && n_out0 + c0 + g + 8 <= Nst)) {
+              if (EPI == EPI_HEADS) {  // column -> (which tensor, head, offset); row -> (batch, token)
+                TT* dst = reinterpret_cast<TT*>(a.outs[h_which]) + ((size_t)(hb * a.heads + h_head) * a.tokens + htok) * a.head_pad + h_off;
                 E::store8(dst, v);
               } else {
-                if (has_res) {
+                if (RES) {
                   float2 f;
                   const uint4 u = res_cur[g >> 3];
                   f = T16<BF16>::unpack(u.x); v[0] += f.x; v[1] += f.y;
@@ -282,13 +305,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                   f = T16<BF16>::unpack(u.z); v[4] += f.x; v[5] += f.y;
                   f = T16<BF16>::unpack(u.w); v[6] += f.x; v[7] += f.y;
                 }
-                E::store8(reinterpret_cast<TT*>(a.out) + (size_t)m * a.ldo + n, v);
+                E::store8(out_row + c0 + g, v);
               }
+            }
+            if (EPI == EPI_HEADS) {
+              h_off += 8;
+              if (h_off >= a.head_dim) { h_off = 0; if (++h_head == a.heads) { h_head = 0; ++h_which; } }
             }
           }
         }
+        if (RES) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
+          for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -349,11 +378,29 @@ int gemm_pick_bn(int M, int N, int K, int epi) {
   return best_bn;
 }
 
+typedef void (*GemmKernel)(const GemmArgs);
+// variant index = bf16 * 6 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu, 5: heads}
+static GemmKernel gemm_variant(int i) {
+  switch (i) {
+    case 0: return gemm_kernel<false, EPI_PLAIN, false, false>;
+    case 1: return gemm_kernel<false, EPI_PLAIN, true, false>;
+    case 2: return gemm_kernel<false, EPI_PLAIN, false, true>;
+    case 3: return gemm_kernel<false, EPI_PLAIN, true, true>;
+    case 4: return gemm_kernel<false, EPI_GEGLU, false, false>;
+    case 5: return gemm_kernel<false, EPI_HEADS, false, false>;
+    case 6: return gemm_kernel<true, EPI_PLAIN, false, false>;
+    case 7: return gemm_kernel<true, EPI_PLAIN, true, false>;
+    case 8: return gemm_kernel<true, EPI_PLAIN, false, true>;
+    case 9: return gemm_kernel<true, EPI_PLAIN, true, true>;
+    case 10: return gemm_kernel<true, EPI_GEGLU, false, false>;
+    default: return gemm_kernel<true, EPI_HEADS, false, false>;
+  }
+}
+
 int gemm_init() {
   static bool done = false;
   if (!done) {
-    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 12; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done = true;
   }
   return 0;
@@ -369,7 +416,9 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   const int tiles = num_m * num_n;
   if (tiles <= 0) return 0;
   const int grid = std::min(tiles, num_sms());
-  auto kern = bf16 ? gemm_kernel<true> : gemm_kernel<false>;
+  int vi = a.epi == EPI_GEGLU ? 4 : (a.epi == EPI_HEADS ? 5 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0)));
+  if ((a.epi != EPI_PLAIN) && (a.residual || a.rowvec)) { set_last_error(__FILE__, __LINE__, "gemm: residual / rowvec need EPI_PLAIN"); return -1; }
+  GemmKernel kern = gemm_variant(vi + (bf16 ? 6 : 0));
   if (gemm_init() != 0) return -1;
   kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
   SDXE_CUDA_CHECK(cudaGetLastError());
