@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
             const uint64_t kd = umma_desc_sw128(k_addr, 16, 1024);
             const int ks = (c == a.dqk_slabs - 1) ? ksteps_last : 4;
-            for (int k = 0; k < ks; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ks) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
             if (q_slot_held) { tc_commit(slot_empty(q_slot)); (void)q_phase; }
             release();
           }
@@ -155,16 +157,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           mbar_wait(p_ready(j & 1), (uint32_t)((j >> 1) & 1));
           tc_fence_after();
           const uint32_t sPj = sP + (uint32_t)(j & 1) * 2 * SLAB_BYTES;
+          const uint64_t pd0 = umma_desc_sw128(sPj, 16, 1024), pd1 = umma_desc_sw128(sPj + SLAB_BYTES, 16, 1024);
           for (int vs = 0; vs < a.dv_slabs; ++vs) {
             const uint32_t v_addr = pop();
             tc_fence_after();
             const uint32_t d_o = tmem_base + TM_O + (uint32_t)(vs * 64);
+            const uint64_t vd = umma_desc_sw128(v_addr, SLAB_BYTES, 1024);
+            const uint32_t id = (vs == a.dv_slabs - 1) ? idesc_pv_last : idesc_pv;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t pd = umma_desc_sw128(sPj + (k >> 2) * SLAB_BYTES, 16, 1024) + 2 * (k & 3);
-              const uint64_t vd = umma_desc_sw128(v_addr + k * 2048, SLAB_BYTES, 1024);
-              tc_mma_f16(d_o, pd, vd, (vs == a.dv_slabs - 1) ? idesc_pv_last : idesc_pv, (j | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < 8; ++k)  // +16 key rows: +128 in V's addr>>4 field, +2 in P's
+              tc_mma_f16(d_o, (k < 4 ? pd0 : pd1) + 2 * (k & 3), vd + 128 * k, id, (j | k) != 0 ? 1u : 0u);
             release();
           }
           tc_commit(pv_done(j & 1));

@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       const uint32_t idesc_pv_last = umma_idesc(BF16 ? 1 : 0, 128, n_last, 0, 1);
       int slot = 0;
       uint32_t phase = 0;
+      // The issuing thread is a single lane: every instruction it spends on descriptor arithmetic delays S / PV for
+      // 256 softmax threads. All descriptors are therefore built once (Q, P: constant per CTA) or once per slab
+      // (K, V: at pop time); inside the MMA loops only a 64-bit add remains. Loops have constant bounds (<= 2 slabs)
+      // so nothing is indexed dynamically.
       auto pop = [&](int& slot_id) -> uint32_t {  // wait for the next slab in ring order; caller releases it later
         mbar_wait(slot_full(slot), phase);
         slot_id = slot;
@@ -104,51 +108,78 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         if (++slot == NS) { slot = 0; phase ^= 1u; }
         return addr;
       };
-      auto issue_s = [&](int t, const uint32_t* k_addr) {
+      uint64_t qd[2][2], pd[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          qd[t][c] = umma_desc_sw128(sQ + (t * QS + c) * SLAB2, 16, 1024);
+          pd[t][c] = umma_desc_sw128(sP + (uint32_t)(t * 2 + c) * SLAB2, 16, 1024);
+        }
+      }
+      uint64_t kd[2] = {0, 0}, vd[2] = {0, 0};
+      int k_slot[2] = {0, 0}, v_slot[2] = {0, 0};
+      auto issue_s = [&](int t) {
         const uint32_t d_s = tmem_base + (uint32_t)(t * 128);
-        for (int c = 0; c < QS; ++c) {
-          const uint64_t qd = umma_desc_sw128(sQ + (t * QS + c) * SLAB2, 16, 1024);
-          const uint64_t kd = umma_desc_sw128(k_addr[c], 16, 1024);
-          const int ks = (c == QS - 1) ? ksteps_last : 4;
-          for (int k = 0; k < ks; ++k) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < QS) {
+            const int ks = (c == QS - 1) ? ksteps_last : 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ks) tc_mma_f16(d_s, qd[t][c] + 2 * k, kd[c] + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+          }
         }
         tc_commit(s_full(t));
       };
-      auto issue_pv = [&](int t, const uint32_t* v_addr, int j) {
-        const uint32_t sPt = sP + (uint32_t)t * 2 * SLAB2;
-        for (int vs = 0; vs < VS; ++vs) {
-          const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
+      auto issue_pv = [&](int t, int j) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t pd = umma_desc_sw128(sPt + (k >> 2) * SLAB2, 16, 1024) + 2 * (k & 3);
-            const uint64_t vd = umma_desc_sw128(v_addr[vs] + k * 2048, SLAB2, 1024);
-            tc_mma_f16(d_o, pd, vd, (vs == VS - 1) ? idesc_pv_last : idesc_pv, (j | k) != 0 ? 1u : 0u);
+        for (int vs = 0; vs < 2; ++vs) {
+          if (vs < VS) {
+            const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
+            const uint32_t id = (vs == VS - 1) ? idesc_pv_last : idesc_pv;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // 16 key rows per step: +2048 B in V (= +128 in the addr>>4 field), +32 B in P
+              tc_mma_f16(d_o, pd[t][k >> 2] + 2 * (k & 3), vd[vs] + 128 * k, id, (j | k) != 0 ? 1u : 0u);
           }
         }
         tc_commit(pv_done(t));
       };
-      uint32_t k_addr[2], v_addr[2];
-      int k_slot[2], v_slot[2];
       mbar_wait(q_full, 0);
-      for (int c = 0; c < QS; ++c) k_addr[c] = pop(k_slot[c]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < QS) kd[c] = umma_desc_sw128(pop(k_slot[c]), 16, 1024);
       tc_fence_after();
-      issue_s(0, k_addr);
-      issue_s(1, k_addr);
-      for (int c = 0; c < QS; ++c) tc_commit(slot_empty(k_slot[c]));
+      issue_s(0);
+      issue_s(1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < QS) tc_commit(slot_empty(k_slot[c]));
       for (int i = 0; i < nblk; ++i) {
         const bool more = i + 1 < nblk;
-        if (more)
-          for (int c = 0; c < QS; ++c) k_addr[c] = pop(k_slot[c]);
-        for (int vs = 0; vs < VS; ++vs) v_addr[vs] = pop(v_slot[vs]);
+        if (more) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < QS) kd[c] = umma_desc_sw128(pop(k_slot[c]), 16, 1024);
+        }
+#pragma unroll
+        for (int vs = 0; vs < 2; ++vs)
+          if (vs < VS) vd[vs] = umma_desc_sw128(pop(v_slot[vs]), SLAB2, 1024);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
           mbar_wait(p_ready(t), (uint32_t)(i & 1));
           tc_fence_after();
-          if (more) issue_s(t, k_addr);
-          issue_pv(t, v_addr, i);
+          if (more) issue_s(t);
+          issue_pv(t, i);
         }
-        if (more)
-          for (int c = 0; c < QS; ++c) tc_commit(slot_empty(k_slot[c]));
-        for (int vs = 0; vs < VS; ++vs) tc_commit(slot_empty(v_slot[vs]));
+        if (more) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < QS) tc_commit(slot_empty(k_slot[c]));
+        }
+#pragma unroll
+        for (int vs = 0; vs < 2; ++vs)
+          if (vs < VS) tc_commit(slot_empty(v_slot[vs]));
       }
     }
   } else {

@@ -91,19 +91,27 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint
 
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int n_img, int chunks,
                                    int groups, float inv_cnt, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per (image, group): lanes stride over the block partials, fixed-order tree reduce (deterministic)
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_img * groups) return;
   const int n = i / groups, g = i - n * groups;
   float a = 0.f, b = 0.f;
-  for (int ch = 0; ch < chunks; ++ch) {
-    const float* src = partial + (((size_t)n * chunks + ch) * groups + g) * 2;
-    a += src[0];
-    b += src[1];
+  for (int ch = lane; ch < chunks; ch += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((size_t)n * chunks + ch) * groups + g) * 2));
+    a += v.x;
+    b += v.y;
   }
-  const float mean = a * inv_cnt;
-  const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = rsqrtf(var + eps);
+  }
 }
 
 template <bool BF16, bool SILU>
@@ -179,7 +187,7 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
     gn_stats_kernel<false><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb);
   SDXE_LAUNCH_CHECK();
   const float inv_cnt = 1.f / ((float)hw * (float)(C / groups));
-  gn_finalize_kernel<<<(n * groups + 127) / 128, 128, 0, s>>>(partial, stats, n, chunks, groups, inv_cnt, eps);
+  gn_finalize_kernel<<<(n * groups + 3) / 4, 128, 0, s>>>(partial, stats, n, chunks, groups, inv_cnt, eps);
   SDXE_LAUNCH_CHECK();
   const size_t total = (size_t)n * hw * V;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
