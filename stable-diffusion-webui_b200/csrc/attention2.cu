@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
     const uint32_t p_row = sP + (uint32_t)t * 2 * SLAB2 + row * 128;
     const float sl2 = a.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
+    // The exp phases of the two tiles are forced to alternate (named barriers 2 / 3 as a token): the MUFU pipe is the
+    // scarce unit, so tile A exponentiates while tile B loads / reduces its next score block, and vice versa. Without
+    // the token both tiles drift into phase, share the pipe, and then idle it together.
+    const uint32_t my_turn = 2u + (uint32_t)t, other_turn = 3u - (uint32_t)t;
+    if (t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile A goes first
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(s_full(t), (uint32_t)(i & 1));
       tc_fence_after();
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       }
       const float mb = m_run * sl2;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      asm volatile("bar.sync %0, 256;" ::"r"(my_turn) : "memory");
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 0]), sl2, -mb));
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
                      "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
                      : "memory");
       }
+      if (!(t == 1 && i == nblk - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(other_turn) : "memory");
       l_run += (s0 + s1) + (s2 + s3);
       tc_fence_before();
       fence_proxy_async_smem();

@@ -91,7 +91,8 @@ int sdxe_gemm(const void* A, const void* W, void* out, int M, int N, int K, cons
   a.num_stages = gemm_pick_stages(a.BN);
   if (make_tmap_2d(&a.tmA, A, M, K, K, 128)) return -1;
   a.tmA2 = a.tmA;
-  if (make_tmap_2d(&a.tmB, Wp, N, K, K, a.BN)) return -1;
+  a.cluster = gemm_pick_cluster(a.M, a.BN);
+  if (make_tmap_2d(&a.tmB, Wp, N, K, K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bp;
   a.residual = residual;
   a.ldr = N;
@@ -120,7 +121,8 @@ int sdxe_conv3x3_nhwc(const void* x, const void* w, void* out, int n, int h, int
   a.num_stages = gemm_pick_stages(a.BN);
   if (make_tmap_nhwc(&a.tmA, x, n, h, wd, cin, bw, bh, bn)) return -1;
   a.tmA2 = a.tmA;
-  if (make_tmap_2d(&a.tmB, w, cout, a.K, a.K, a.BN)) return -1;
+  a.cluster = gemm_pick_cluster(a.M, a.BN);
+  if (make_tmap_2d(&a.tmB, w, cout, a.K, a.K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bias;
   a.out = out;
   a.ldo = cout;

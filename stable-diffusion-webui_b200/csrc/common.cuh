@@ -104,6 +104,23 @@ SDXE_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, i
       : "memory");
 }
 
+// multicast variant: the box lands at the same smem offset in every CTA of `mask`, each CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes written into it
+SDXE_DEVINL void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+SDXE_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SDXE_DEVINL void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit, MMA, ld/st
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +136,10 @@ SDXE_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sy
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete.
 SDXE_DEVINL void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (smem slot shared through TMA multicast)
+SDXE_DEVINL void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit inputs, fp32 accumulate.
 SDXE_DEVINL void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

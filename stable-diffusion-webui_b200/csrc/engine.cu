@@ -251,7 +251,8 @@ struct Builder {
     ECHK(make_tmap_2d(&a.tmA, A, M, a.K1, lda, 128));
     if (o.A2) ECHK(make_tmap_2d(&a.tmA2, o.A2, M, W.K - o.K1, W.K - o.K1, 128));
     else a.tmA2 = a.tmA;
-    ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), W.K, W.ld, a.BN));
+    a.cluster = gemm_pick_cluster(a.M, a.BN);
+    ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), W.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
     a.bias = W.b;
     a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
     a.residual = o.residual; a.ldr = o.ldr;
@@ -283,7 +284,8 @@ struct Builder {
       a.num_stages = gemm_pick_stages(a.BN);
       ECHK(make_tmap_nhwc(&a.tmA, x.p, x.n, x.h, x.w, x.c, bw, bh, bn));
       a.tmA2 = a.tmA;
-      ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), a.K, W.ld, a.BN));
+      a.cluster = gemm_pick_cluster(a.M, a.BN);
+      ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), a.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
       a.bias = W.b;
       a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
       a.residual = o.residual; a.ldr = o.ldr;

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace sdxe {
 
@@ -93,13 +94,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (a.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+  // Work enumeration. cluster == 1: tile t -> (m_blk, n_blk) = (t / num_n, t % num_n), CTA stride gridDim.x.
+  // cluster == 2: the CTA pair walks tile PAIRS p -> m_blk = 2 * (p / num_n) + rank, n_blk = p % num_n; both CTAs
+  // execute the same number of k-blocks in lockstep and each fetches one half of the shared B tile (multicast).
+  const bool clustered = a.cluster == 2;
+  const uint32_t crank = clustered ? cluster_ctarank() : 0u;
+  const int work_first = clustered ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_step = clustered ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = clustered ? (num_m >> 1) * num_n : num_m * num_n;  // work items per CTA walk
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), clustered ? 2 : 1);  // a multicast slot is free when BOTH CTAs' MMAs have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -112,6 +120,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -120,8 +129,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = work_first; tile < num_tiles; tile += work_step) {
+        const int n_blk = tile % num_n;
+        const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
         const int m0 = m_blk * BLOCK_M;
         int img0 = 0, h0 = 0, w0 = 0;
         if (a.conv) {
@@ -146,7 +156,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             if (k0 < a.K1) tma_load_2d(sA, &a.tmA, fb, k0, m0);
             else tma_load_2d(sA, &a.tmA2, fb, k0 - a.K1, m0);
           }
-          tma_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN);
+          if (clustered) {  // my half of the B tile, delivered to both CTAs
+            const int hb = BN >> 1;
+            tma_load_2d_mc(sB + crank * (uint32_t)hb * 128u, &a.tmB, fb, kb * BLOCK_K, n_blk * BN + (int)crank * hb, (uint16_t)3);
+          } else {
+            tma_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN);
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = work_first; tile < num_tiles; tile += work_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -175,7 +190,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             // +32 bytes along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
             tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));
+          if (clustered) tc_commit_mc(empty_bar(stage), (uint16_t)3);
+          else tc_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));
@@ -205,8 +221,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     TT* const outp = reinterpret_cast<TT*>(a.out);
     const float* const biasp = a.bias;
     const int M = a.M, N = a.N, ldo = a.ldo, ldr = a.ldr;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
-      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+    for (int tile = work_first; tile < num_tiles; tile += work_step, ++tile_ctr) {
+      const int n_blk = tile % num_n;
+      const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
       const int m = m_blk * BLOCK_M + row;
       const bool row_ok = m < M;
       const int n_out0 = n_blk * out_cols;  // first output column of this tile
@@ -329,6 +346,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -415,14 +433,44 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
   const int tiles = num_m * num_n;
   if (tiles <= 0) return 0;
-  const int grid = std::min(tiles, num_sms());
+  int grid = std::min(tiles, num_sms());
+  if (a.cluster == 2) {
+    if ((num_m & 1) || (a.BN % 16)) { set_last_error(__FILE__, __LINE__, "gemm: cluster needs an even m-tile count"); return -1; }
+    grid = std::min(tiles, num_sms() & ~1);
+  }
   int vi = a.epi == EPI_GEGLU ? 4 : (a.epi == EPI_HEADS ? 5 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0)));
   if ((a.epi != EPI_PLAIN) && (a.residual || a.rowvec)) { set_last_error(__FILE__, __LINE__, "gemm: residual / rowvec need EPI_PLAIN"); return -1; }
   GemmKernel kern = gemm_variant(vi + (bf16 ? 6 : 0));
   if (gemm_init() != 0) return -1;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
+  if (a.cluster == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SDXE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
+  }
   SDXE_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+// Pair CTAs (TMA multicast of the B tile) when the geometry allows it: halves the weight-tile traffic per CTA.
+int gemm_pick_cluster(int M, int BN) {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 1; }
+  if (!mode) return 1;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  return (num_m % 2 == 0 && num_m >= 2 && BN % 16 == 0 && BN >= 32) ? 2 : 1;
 }
 
 }  // namespace sdxe

@@ -24,7 +24,7 @@ struct alignas(64) GemmArgs {
   int bh, bn;
   int epi;
   int ldrv;          // row pitch (elements) of rowvec
-  int reserved0;
+  int cluster;       // 1, or 2: CTA pairs (consecutive m-tiles, same n-tile) share the B tile through TMA multicast
   const float* bias;    // [N] (EPI_GEGLU: interleaved like the weights) or null
   const float* rowvec;  // [M / rows_per_sample, N] per-sample vector added to every row of the sample, or null
   int rows_per_sample;
@@ -43,6 +43,7 @@ int gemm_init();  // one-time kernel attribute setup (call before any stream cap
 // Tile-width heuristic: pick BN for an [M, N] output (geglu needs BN % 32 == 0 and N % BN == 0).
 int gemm_pick_bn(int M, int N, int K, int epi);
 int gemm_pick_stages(int BN);
+int gemm_pick_cluster(int M, int BN);  // 2 when CTA pairs can share the B tile (TMA multicast), else 1
 // 128-pixel tile of the implicit-GEMM conv as a TMA box (bw x bh x bn); false if (H, W) needs the im2col path.
 bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn);
 
