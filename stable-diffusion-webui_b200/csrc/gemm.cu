@@ -464,10 +464,13 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   return 0;
 }
 
-// Pair CTAs (TMA multicast of the B tile) when the geometry allows it: halves the weight-tile traffic per CTA.
+// Pair CTAs (TMA multicast of the B tile) when the geometry allows it: halves the weight-tile L2 traffic per CTA.
+// Measured on B200 (profiles/r1_notes.md): no gain — the 128 x BN single-CTA tile is bound by shared-memory
+// bandwidth (TMA writes + SS-mode MMA reads of the same 36-48 KB per k-block), not by L2, and multicast still lands
+// the full B tile in both CTAs. Kept (validated, off by default; SDXE_CLUSTER=1) as the scaffold for cta_group::2.
 int gemm_pick_cluster(int M, int BN) {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 1; }
+  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 0; }
   if (!mode) return 1;
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   return (num_m % 2 == 0 && num_m >= 2 && BN % 16 == 0 && BN >= 32) ? 2 : 1;

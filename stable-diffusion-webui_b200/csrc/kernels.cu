@@ -114,40 +114,41 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
   }
 }
 
+// Apply: same thread -> (8-channel vector, pixel row) mapping as the statistics kernel, so the per-channel
+// scale = rstd*gamma and shift = beta - mean*scale are computed once per thread and the pixel loop is
+// load -> 8 x (FMA [+ SiLU]) -> store with no index arithmetic.
 template <bool BF16, bool SILU>
 __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, uint4* __restrict__ out, int n_img, int hw, int groups) {
+                                const float* __restrict__ beta, uint4* __restrict__ out, int hw, int groups,
+                                int pix_per_block) {
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
-  const size_t total = (size_t)n_img * hw * V;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int vec = (int)(idx % V);
-    const size_t pix = idx / V;
-    const int n = (int)(pix / hw);
-    const int c = vec * 8;
-    const uint4 u = (c < c1) ? __ldg(x1 + (pix * c1 + c) / 8) : __ldg(x2 + (pix * c2 + (c - c1)) / 8);
+  const int n = blockIdx.y;
+  const int vec = threadIdx.x % V, prow = threadIdx.x / V, rpi = blockDim.x / V;
+  const int c = vec * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float2 mr = __ldg(reinterpret_cast<const float2*>(stats + ((size_t)n * groups + g) * 2));
+    sc[j] = mr.y * __ldg(gamma + c + j);
+    sh[j] = __ldg(beta + c + j) - mr.x * sc[j];
+  }
+  const uint4* src = (c < c1) ? x1 : x2;
+  const int cs = (c < c1) ? c1 : c2, co = (c < c1) ? c : c - c1;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+#pragma unroll 4
+  for (int p = p0 + prow; p < p1; p += rpi) {
+    const size_t pix = (size_t)n * hw + p;
     float v[8];
-    unpack8<BF16>(u, v);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c)), bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
+    unpack8<BF16>(__ldg(src + (pix * cs + co) / 8), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      if (g != g_prev) {
-        const float2 mr = __ldg(reinterpret_cast<const float2*>(stats + ((size_t)n * groups + g) * 2));
-        mean = mr.x;
-        rstd = mr.y;
-        g_prev = g;
-      }
-      float y = (v[j] - mean) * rstd * gm[j] + bt[j];
+      float y = fmaf(v[j], sc[j], sh[j]);
       if (SILU) y = silu_f(y);
       v[j] = y;
     }
-    out[idx] = pack8<BF16>(v);
+    out[pix * V + vec] = pack8<BF16>(v);
   }
 }
 
@@ -189,11 +190,14 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
   const float inv_cnt = 1.f / ((float)hw * (float)(C / groups));
   gn_finalize_kernel<<<(n * groups + 3) / 4, 128, 0, s>>>(partial, stats, n, chunks, groups, inv_cnt, eps);
   SDXE_LAUNCH_CHECK();
-  const size_t total = (size_t)n * hw * V;
-  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+  // apply: finer pixel chunks than the statistics pass (pure streaming, wants every SM busy several times over)
+  int achunks = std::max(1, std::min((num_sms() * 8 + n - 1) / n, (hw + rpi * 2 - 1) / (rpi * 2)));
+  const int appb = (hw + achunks - 1) / achunks;
+  achunks = (hw + appb - 1) / appb;
+  dim3 agrid(achunks, n);
 #define GN_APPLY(B, S)                                                                                              \
-  gn_apply_kernel<B, S><<<blocks, 256, 0, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, gamma, beta, \
-                                               (uint4*)out, n, hw, groups)
+  gn_apply_kernel<B, S><<<agrid, threads, 0, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, gamma, beta, \
+                                                  (uint4*)out, hw, groups, appb)
   if (bf16) { if (silu) GN_APPLY(true, true); else GN_APPLY(true, false); }
   else { if (silu) GN_APPLY(false, true); else GN_APPLY(false, false); }
 #undef GN_APPLY
@@ -204,10 +208,9 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
 // =============================================================================================================
 // LayerNorm (fp32 statistics, as torch autocast runs layer_norm in fp32) — one warp per row
 // =============================================================================================================
-template <bool BF16>
-__global__ void layer_norm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+template <bool BF16, int MAXV>  // MAXV x 32 x 8 channels held in registers (one global read of the row)
+__global__ void __launch_bounds__(256) layer_norm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, uint4* __restrict__ out, int rows, int C, float eps) {
-  constexpr int MAXV = 8;  // up to 8 x 32 x 8 = 2048 channels held in registers (one global read of the row)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int V = C >> 3;
@@ -257,9 +260,12 @@ __global__ void layer_norm_kernel(const uint4* __restrict__ x, const float* __re
 int layer_norm_launch(const void* x, const float* gamma, const float* beta, void* out, int rows, int c, float eps,
                       bool bf16, cudaStream_t s) {
   if (c % 8 || c > 2048) { set_last_error(__FILE__, __LINE__, "layer_norm: C % 8 != 0 or C > 2048"); return -1; }
-  const int blocks = (rows + 3) / 4;
-  if (bf16) layer_norm_kernel<true><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
-  else layer_norm_kernel<false><<<blocks, 128, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps);
+  const int blocks = (rows + 7) / 8;  // 8 warps (rows) per block
+  const int nv = (c / 8 + 31) / 32;   // vectors per lane
+#define LN_LAUNCH(B, MV) layer_norm_kernel<B, MV><<<blocks, 256, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps)
+  if (bf16) { if (nv <= 2) LN_LAUNCH(true, 2); else if (nv <= 3) LN_LAUNCH(true, 3); else if (nv <= 5) LN_LAUNCH(true, 5); else LN_LAUNCH(true, 8); }
+  else { if (nv <= 2) LN_LAUNCH(false, 2); else if (nv <= 3) LN_LAUNCH(false, 3); else if (nv <= 5) LN_LAUNCH(false, 5); else LN_LAUNCH(false, 8); }
+#undef LN_LAUNCH
   SDXE_LAUNCH_CHECK();
   return 0;
 }
