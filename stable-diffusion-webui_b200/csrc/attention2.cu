@@ -5,8 +5,8 @@
 //    L2 -> shared-memory traffic per FLOP. With small head dims (SD1.5: d = 40) a 128-row tile is L2-bound at
 //    ~80 FLOP/byte; this kernel doubles that.
 //  * the two tiles ping-pong on the tensor pipe: while tile A's rows are in their softmax, the MMA thread issues tile
-//    B's S and PV, and vice versa (the FA-4 schedule). Warps 2-5 are tile A's softmax (one thread per row), warps
-//    6-9 tile B's, so every scheduler interleaves two softmax warps.
+//    B's S and PV, and vice versa (the FA-4 schedule). 16 softmax warps (tile x column-half x lane quarter): every
+//    scheduler interleaves four of them.
 //  * TMEM: S_A | S_B | O_A | O_B at columns 0 / 128 / 256 / 384 (fp32, 128 columns each).
 //
 // Barrier protocol (all single-phase-per-iteration, parity = i & 1):
@@ -19,10 +19,10 @@
 namespace sdxe {
 
 static constexpr int SLAB2 = 16384;
-static constexpr int ATT2_THREADS = 320;
+static constexpr int ATT2_THREADS = 576;  // warp 0 TMA, warp 1 MMA, 16 softmax warps
 
 template <bool BF16>
-__global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __maxnreg__(112) attention2_kernel(const __grid_constant__ AttnArgs a) {
   using T = T16<BF16>;
   using TT = typename T::type;
   extern __shared__ uint8_t smem_raw[];
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
   auto p_ready = [&](int t) { return bar_base + 8u * (2 * NS + 3 + t); };
   auto pv_done = [&](int t) { return bar_base + 8u * (2 * NS + 5 + t); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7));
+  float* xch = reinterpret_cast<float*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7) + 16);  // row max / sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
     mbar_init(q_full, 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_ready(t), 4); mbar_init(pv_done(t), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_ready(t), 8); mbar_init(pv_done(t), 1); }
     fence_mbar_init();
     tma_prefetch_desc(&a.tmQ);
     tma_prefetch_desc(&a.tmK);
@@ -183,55 +184,61 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax / epilogue (one thread per row)
+    // ---------------------------------------------------------------- softmax / epilogue
+    // 16 warps: (tile, column half) x 4 lane quarters. A query row of a tile is shared by two threads (warps w and
+    // w + 8 own the same TMEM lane quarter of the same tile); one takes key columns 0-63 of the block, the other
+    // 64-127. Four softmax warps per scheduler keep the MUFU / FMA pipes busy through each other's latencies; the
+    // softmax is latency-bound with fewer (measured: 1 or 2 warps per scheduler -> ~35 % issue utilisation).
+    const int sw = warp - 2;
     const int quarter = warp & 3;
-    const int t = (warp - 2) >> 2;  // tile
+    const int t = (sw >> 2) & 1;   // tile
+    const int half = sw >> 3;      // column half
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + (uint32_t)(t * 128) + lane_base;
+    const uint32_t t_s = tmem_base + (uint32_t)(t * 128 + half * 64) + lane_base;
     const uint32_t t_o = tmem_base + 256u + (uint32_t)(t * 128) + lane_base;
-    const uint32_t p_row = sP + (uint32_t)t * 2 * SLAB2 + row * 128;
+    const uint32_t p_row = sP + (uint32_t)(t * 2 + half) * SLAB2 + row * 128;  // K-major swizzle atom `half` of P_t
+    const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + quarter);               // the two warps sharing these 32 rows
+    float* xq = xch + t * 256;                                                 // [2 buf][2 tiles][2 halves][128]
     const float sl2 = a.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    // The exp phases of the two tiles are forced to alternate (named barriers 2 / 3 as a token): the MUFU pipe is the
-    // scarce unit, so tile A exponentiates while tile B loads / reduces its next score block, and vice versa. Without
-    // the token both tiles drift into phase, share the pipe, and then idle it together.
-    const uint32_t my_turn = 2u + (uint32_t)t, other_turn = 3u - (uint32_t)t;
-    if (t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile A goes first
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(s_full(t), (uint32_t)(i & 1));
       tc_fence_after();
-      const int kv0 = i * 128;
-      uint32_t sreg[128];
+      const int kv0 = i * 128 + half * 64;
+      uint32_t sreg[64];
       tmem_ld32(t_s, sreg);
       tmem_ld32(t_s + 32, sreg + 32);
-      tmem_ld32(t_s + 64, sreg + 64);
-      tmem_ld32(t_s + 96, sreg + 96);
       tc_wait_ld();
-      if (kv0 + 128 > a.Nk) {
+      if (kv0 + 64 > a.Nk) {
 #pragma unroll
-        for (int j = 0; j < 128; ++j)
+        for (int j = 0; j < 64; ++j)
           if (kv0 + j >= a.Nk) sreg[j] = 0xff800000u;  // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 128; j += 4) {
+      for (int j = 0; j < 64; j += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(sreg[j]));
         mx1 = fmaxf(mx1, __uint_as_float(sreg[j + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(sreg[j + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(sreg[j + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // agree on the row max with the thread that owns the other 64 columns
+      float* xb = xq + (i & 1) * 512;
+      xb[half * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       const float m_cand = fmaxf(m_run, mx);
       const bool need = (m_cand - m_run) * sl2 > 8.f;  // lazy rescale (first block: +inf > 8)
       if (i >= 1) {
         mbar_wait(pv_done(t), (uint32_t)((i - 1) & 1));  // O_T holds blocks < i, P_T buffer free
         tc_fence_after();
       }
-      if (__any_sync(0xffffffffu, need)) {
+      if (__any_sync(0xffffffffu, need)) {  // same rows, same decision in both warps of the pair
         const float alpha = ex2_approx((m_run - m_cand) * sl2);
         if (i >= 1) {
-          for (int c = 0; c < a.dv_slabs * 2; ++c) {
+          for (int c = half * a.dv_slabs; c < (half + 1) * a.dv_slabs; ++c) {  // each half rescales its O columns
             uint32_t r[32];
             tmem_ld32(t_o + c * 32, r);
             tc_wait_ld();
@@ -246,9 +253,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       }
       const float mb = m_run * sl2;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      asm volatile("bar.sync %0, 256;" ::"r"(my_turn) : "memory");
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 0]), sl2, -mb));
         const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 1]), sl2, -mb));
         const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 2]), sl2, -mb));
@@ -258,27 +264,32 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         const float p6 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 6]), sl2, -mb));
         const float p7 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 7]), sl2, -mb));
         s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
-        // P tile = two K-major 128B-swizzle atoms of 64 key columns; 16-byte chunk q of this row
-        const uint32_t chunk = (uint32_t)(q & 7) ^ (uint32_t)(row & 7);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (q >> 3) * SLAB2 + chunk * 16),
+        const uint32_t chunk = (uint32_t)q ^ (uint32_t)(row & 7);  // 16-byte chunk q of this row, 128B swizzle
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
                      "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
                      : "memory");
       }
-      if (!(t == 1 && i == nblk - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(other_turn) : "memory");
       l_run += (s0 + s1) + (s2 + s3);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(t));
     }
-    // ---- epilogue
+    // ---- epilogue: the row sum is the sum of the two halves' partial sums
+    {
+      float* xb = xq + (nblk & 1) * 512;
+      xb[half * 128 + row] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l_run += xb[(half ^ 1) * 128 + row];
+    }
     mbar_wait(pv_done(t), (uint32_t)((nblk - 1) & 1));
     tc_fence_after();
     const int q = q0 + t * 128 + row;
     const float inv_l = 1.f / l_run;
     const int b = bh / a.H, h = bh - b * a.H;
     TT* orow = reinterpret_cast<TT*>(a.out) + ((size_t)b * a.Nq + q) * a.ldo + a.out_col0 + h * a.dv;
-    for (int c = 0; c * 32 < a.dv; ++c) {
+    for (int c = half * a.dv_slabs; c < (half + 1) * a.dv_slabs; ++c) {
+      if (c * 32 >= a.dv) break;
       uint32_t r[32];
       tmem_ld32(t_o + c * 32, r);
       tc_wait_ld();
@@ -326,7 +337,7 @@ int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   a.q_resident = 1;
   a.num_slots = std::min(10, budget - 4 - 2 * a.dqk_slabs);
   if (a.num_slots < a.dqk_slabs + a.dv_slabs + 1) { set_last_error(__FILE__, __LINE__, "attention2: smem"); return -1; }
-  const size_t smem = (size_t)(2 * a.dqk_slabs + a.num_slots + 4) * SLAB2 + 8 * (2 * a.num_slots + 7) + 16 + 1024;
+  const size_t smem = (size_t)(2 * a.dqk_slabs + a.num_slots + 4) * SLAB2 + 8 * (2 * a.num_slots + 7) + 16 + 4096 + 1024;
   if (attention2_init() != 0) return -1;
   auto kern = bf16 ? attention2_kernel<true> : attention2_kernel<false>;
   dim3 grid((a.Nq + 255) / 256, a.B * a.H);

@@ -68,7 +68,7 @@ struct Epi {
 
 // EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
-template <bool BF16, int EPI, bool RES, bool ROWVEC>
+template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
   using E = Epi<BF16>;
   using TT = typename T16<BF16>::type;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   // Work enumeration. cluster == 1: tile t -> (m_blk, n_blk) = (t / num_n, t % num_n), CTA stride gridDim.x.
   // cluster == 2: the CTA pair walks tile PAIRS p -> m_blk = 2 * (p / num_n) + rank, n_blk = p % num_n; both CTAs
   // execute the same number of k-blocks in lockstep and each fetches one half of the shared B tile (multicast).
-  const bool clustered = a.cluster == 2;
+  constexpr bool clustered = CLUSTER;  // compile-time: the default (unpaired) kernel carries none of this
   const uint32_t crank = clustered ? cluster_ctarank() : 0u;
   const int work_first = clustered ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_step = clustered ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -397,28 +397,28 @@ int gemm_pick_bn(int M, int N, int K, int epi) {
 }
 
 typedef void (*GemmKernel)(const GemmArgs);
-// variant index = bf16 * 6 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu, 5: heads}
-static GemmKernel gemm_variant(int i) {
-  switch (i) {
-    case 0: return gemm_kernel<false, EPI_PLAIN, false, false>;
-    case 1: return gemm_kernel<false, EPI_PLAIN, true, false>;
-    case 2: return gemm_kernel<false, EPI_PLAIN, false, true>;
-    case 3: return gemm_kernel<false, EPI_PLAIN, true, true>;
-    case 4: return gemm_kernel<false, EPI_GEGLU, false, false>;
-    case 5: return gemm_kernel<false, EPI_HEADS, false, false>;
-    case 6: return gemm_kernel<true, EPI_PLAIN, false, false>;
-    case 7: return gemm_kernel<true, EPI_PLAIN, true, false>;
-    case 8: return gemm_kernel<true, EPI_PLAIN, false, true>;
-    case 9: return gemm_kernel<true, EPI_PLAIN, true, true>;
-    case 10: return gemm_kernel<true, EPI_GEGLU, false, false>;
-    default: return gemm_kernel<true, EPI_HEADS, false, false>;
+// variant index = cluster * 12 + bf16 * 6 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu, 5: heads}
+template <bool BF16, bool CL>
+static GemmKernel gemm_variant_e(int e) {
+  switch (e) {
+    case 0: return gemm_kernel<BF16, EPI_PLAIN, false, false, CL>;
+    case 1: return gemm_kernel<BF16, EPI_PLAIN, true, false, CL>;
+    case 2: return gemm_kernel<BF16, EPI_PLAIN, false, true, CL>;
+    case 3: return gemm_kernel<BF16, EPI_PLAIN, true, true, CL>;
+    case 4: return gemm_kernel<BF16, EPI_GEGLU, false, false, CL>;
+    default: return gemm_kernel<BF16, EPI_HEADS, false, false, CL>;
   }
+}
+static GemmKernel gemm_variant(int i) {
+  const int cl = i / 12, bf = (i % 12) / 6, e = i % 6;
+  if (cl) return bf ? gemm_variant_e<true, true>(e) : gemm_variant_e<false, true>(e);
+  return bf ? gemm_variant_e<true, false>(e) : gemm_variant_e<false, false>(e);
 }
 
 int gemm_init() {
   static bool done = false;
   if (!done) {
-    for (int i = 0; i < 12; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 24; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done = true;
   }
   return 0;
@@ -440,7 +440,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   }
   int vi = a.epi == EPI_GEGLU ? 4 : (a.epi == EPI_HEADS ? 5 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0)));
   if ((a.epi != EPI_PLAIN) && (a.residual || a.rowvec)) { set_last_error(__FILE__, __LINE__, "gemm: residual / rowvec need EPI_PLAIN"); return -1; }
-  GemmKernel kern = gemm_variant(vi + (bf16 ? 6 : 0));
+  GemmKernel kern = gemm_variant(vi + (bf16 ? 6 : 0) + (a.cluster == 2 ? 12 : 0));
   if (gemm_init() != 0) return -1;
   if (a.cluster == 2) {
     cudaLaunchConfig_t cfg;
