@@ -22,7 +22,7 @@ static constexpr int SLAB2 = 16384;
 static constexpr int ATT2_THREADS = 576;  // warp 0 TMA, warp 1 MMA, 16 softmax warps
 
 template <bool BF16>
-__global__ void __maxnreg__(112) attention2_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnArgs a) {
   using T = T16<BF16>;
   using TT = typename T::type;
   extern __shared__ uint8_t smem_raw[];
@@ -206,22 +206,27 @@ __global__ void __maxnreg__(112) attention2_kernel(const __grid_constant__ AttnA
       mbar_wait(s_full(t), (uint32_t)(i & 1));
       tc_fence_after();
       const int kv0 = i * 128 + half * 64;
-      uint32_t sreg[64];
-      tmem_ld32(t_s, sreg);
-      tmem_ld32(t_s + 32, sreg + 32);
-      tc_wait_ld();
-      if (kv0 + 64 > a.Nk) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j)
-          if (kv0 + j >= a.Nk) sreg[j] = 0xff800000u;  // -inf
-      }
+      const bool tail = kv0 + 64 > a.Nk;  // only the last block has invalid key columns
+      // Two passes over this thread's 64 scores, 32 at a time (TMEM reads are cheap; holding all 64 in registers
+      // does not fit the 96-register budget of a 576-thread CTA and spills).
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sreg[j]));
-        mx1 = fmaxf(mx1, __uint_as_float(sreg[j + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sreg[j + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sreg[j + 3]));
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+        if (tail) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(r[j]));
+          mx1 = fmaxf(mx1, __uint_as_float(r[j + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(r[j + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(r[j + 3]));
+        }
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // agree on the row max with the thread that owns the other 64 columns
@@ -254,20 +259,31 @@ __global__ void __maxnreg__(112) attention2_kernel(const __grid_constant__ AttnA
       const float mb = m_run * sl2;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 0]), sl2, -mb));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 1]), sl2, -mb));
-        const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 2]), sl2, -mb));
-        const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 3]), sl2, -mb));
-        const float p4 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 4]), sl2, -mb));
-        const float p5 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 5]), sl2, -mb));
-        const float p6 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 6]), sl2, -mb));
-        const float p7 = ex2_approx(fmaf(__uint_as_float(sreg[q * 8 + 7]), sl2, -mb));
-        s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
-        const uint32_t chunk = (uint32_t)q ^ (uint32_t)(row & 7);  // 16-byte chunk q of this row, 128B swizzle
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
-                     "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
-                     : "memory");
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+        if (tail) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb));
+          const float p4 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb));
+          const float p5 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb));
+          const float p6 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb));
+          const float p7 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb));
+          s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
+          const uint32_t chunk = (uint32_t)(c * 4 + q) ^ (uint32_t)(row & 7);  // 16-byte chunk of this row, 128B swizzle
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                       "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
+                       : "memory");
+        }
       }
       l_run += (s0 + s1) + (s2 + s3);
       tc_fence_before();
