@@ -207,27 +207,58 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       tc_fence_after();
       const int kv0 = i * 128 + half * 64;
       const bool tail = kv0 + 64 > a.Nk;  // only the last block has invalid key columns
-      // Two passes over this thread's 64 scores, 32 at a time (TMEM reads are cheap; holding all 64 in registers
-      // does not fit the 96-register budget of a 576-thread CTA and spills).
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
-        if (tail) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(r[j]));
-          mx1 = fmaxf(mx1, __uint_as_float(r[j + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(r[j + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(r[j + 3]));
-        }
+      if (i >= 1) {
+        mbar_wait(pv_done(t), (uint32_t)((i - 1) & 1));  // O_T holds blocks < i, P_T buffer free
+        tc_fence_after();
       }
+      // TMEM reads run at ~64 B/clk/SM: one pass over the 128 x 128 fp32 score tile costs as much as its 16 K exp2 on
+      // the MUFU pipe, so the scores must be read ONCE. The running max is kept stale on purpose (lazy rescale), which
+      // lets the common case exponentiate against it in the same pass that finds the block max; only when the block
+      // max beats the stale one by more than 2^8 (first block, then rarely) is the pass repeated with the new max.
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      auto pass = [&](float mb, bool with_max) {
+        s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_s + c * 32, r);
+          tc_wait_ld();
+          if (tail) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;  // -inf
+          }
+          if (with_max) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(r[j]));
+              mx1 = fmaxf(mx1, __uint_as_float(r[j + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(r[j + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(r[j + 3]));
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb));
+            const float p4 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb));
+            const float p5 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb));
+            const float p6 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb));
+            const float p7 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb));
+            s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
+            const uint32_t chunk = (uint32_t)(c * 4 + q) ^ (uint32_t)(row & 7);  // 16-byte chunk of this row, 128B swizzle
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                         "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
+                         : "memory");
+          }
+        }
+      };
+      // speculative pass against the stale max (first block: m_run = -inf -> mb = -inf -> p = inf/NaN garbage that the
+      // mandatory redo below overwrites; the sums are recomputed by the redo as well)
+      pass(i == 0 ? 0.f : m_run * sl2, true);
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // agree on the row max with the thread that owns the other 64 columns
       float* xb = xq + (i & 1) * 512;
@@ -235,11 +266,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       const float m_cand = fmaxf(m_run, mx);
-      const bool need = (m_cand - m_run) * sl2 > 8.f;  // lazy rescale (first block: +inf > 8)
-      if (i >= 1) {
-        mbar_wait(pv_done(t), (uint32_t)((i - 1) & 1));  // O_T holds blocks < i, P_T buffer free
-        tc_fence_after();
-      }
+      const bool need = (m_cand - m_run) * sl2 > 8.f;  // first block: +inf > 8
       if (__any_sync(0xffffffffu, need)) {  // same rows, same decision in both warps of the pair
         const float alpha = ex2_approx((m_run - m_cand) * sl2);
         if (i >= 1) {
@@ -255,35 +282,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         }
         l_run *= alpha;
         m_run = m_cand;
-      }
-      const float mb = m_run * sl2;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
-        if (tail) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb));
-          const float p4 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb));
-          const float p5 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb));
-          const float p6 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb));
-          const float p7 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb));
-          s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
-          const uint32_t chunk = (uint32_t)(c * 4 + q) ^ (uint32_t)(row & 7);  // 16-byte chunk of this row, 128B swizzle
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
-                       "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
-                       : "memory");
-        }
+        pass(m_run * sl2, false);  // redo this block against the new max
       }
       l_run += (s0 + s1) + (s2 + s3);
       tc_fence_before();

@@ -92,6 +92,7 @@ int sdxe_gemm(const void* A, const void* W, void* out, int M, int N, int K, cons
   if (make_tmap_2d(&a.tmA, A, M, K, K, 128)) return -1;
   a.tmA2 = a.tmA;
   a.cluster = gemm_pick_cluster(a.M, a.BN);
+    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
   if (make_tmap_2d(&a.tmB, Wp, N, K, K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bp;
   a.residual = residual;
@@ -122,6 +123,7 @@ int sdxe_conv3x3_nhwc(const void* x, const void* w, void* out, int n, int h, int
   if (make_tmap_nhwc(&a.tmA, x, n, h, wd, cin, bw, bh, bn)) return -1;
   a.tmA2 = a.tmA;
   a.cluster = gemm_pick_cluster(a.M, a.BN);
+    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
   if (make_tmap_2d(&a.tmB, w, cout, a.K, a.K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bias;
   a.out = out;

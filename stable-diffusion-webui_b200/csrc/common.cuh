@@ -112,6 +112,31 @@ SDXE_DEVINL void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms. The mbarrier operand of a pair TMA load is a shared::cluster address whose
+// "peer bit" (bit 24) selects the CTA of the pair; clearing it makes both CTAs' loads signal the LEADER's barrier
+// (cute/arch/copy_sm100_tma.hpp: Sm100MmaPeerBitMask).
+static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+SDXE_DEVINL void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+SDXE_DEVINL void tma2_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+SDXE_DEVINL void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
 SDXE_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -140,6 +165,26 @@ SDXE_DEVINL void tc_commit(uint32_t bar) {
 // same, arriving on the barrier at this offset in every CTA of `mask` (smem slot shared through TMA multicast)
 SDXE_DEVINL void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// ---- cta_group::2: one MMA spans the CTA pair (M = 256: 128 accumulator rows in each CTA's TMEM; A from each CTA's
+// own smem, B rows split half / half across the two CTAs' smem). Issued by the leader CTA only.
+SDXE_DEVINL void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {  // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+SDXE_DEVINL void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+SDXE_DEVINL void tc2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+SDXE_DEVINL void tc2_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit inputs, fp32 accumulate.
 SDXE_DEVINL void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

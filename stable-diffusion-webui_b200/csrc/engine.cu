@@ -252,6 +252,7 @@ struct Builder {
     if (o.A2) ECHK(make_tmap_2d(&a.tmA2, o.A2, M, W.K - o.K1, W.K - o.K1, 128));
     else a.tmA2 = a.tmA;
     a.cluster = gemm_pick_cluster(a.M, a.BN);
+    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
     ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), W.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
     a.bias = W.b;
     a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
@@ -285,6 +286,7 @@ struct Builder {
       ECHK(make_tmap_nhwc(&a.tmA, x.p, x.n, x.h, x.w, x.c, bw, bh, bn));
       a.tmA2 = a.tmA;
       a.cluster = gemm_pick_cluster(a.M, a.BN);
+    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
       ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), a.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
       a.bias = W.b;
       a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);

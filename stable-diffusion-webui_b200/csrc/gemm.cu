@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   const int S = a.num_stages;
   const int BN = a.BN;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)BN * 128u;
+  // paired (cta_group::2): each CTA keeps its own A tile and HALF of the B tile
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)(CLUSTER ? (BN >> 1) : BN) * 128u;
   const uint32_t bar_base = smem_base + S * stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -95,9 +96,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (a.N + BN - 1) / BN;
   const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
-  // Work enumeration. cluster == 1: tile t -> (m_blk, n_blk) = (t / num_n, t % num_n), CTA stride gridDim.x.
-  // cluster == 2: the CTA pair walks tile PAIRS p -> m_blk = 2 * (p / num_n) + rank, n_blk = p % num_n; both CTAs
-  // execute the same number of k-blocks in lockstep and each fetches one half of the shared B tile (multicast).
+  // Work enumeration. Unpaired: tile t -> (m_blk, n_blk) = (t / num_n, t % num_n), CTA stride gridDim.x.
+  // Paired (CLUSTER, cta_group::2): the CTA pair walks 256-row tile pairs p -> m_blk = 2 * (p / num_n) + rank,
+  // n_blk = p % num_n. Both CTAs load (own A rows, own half of B) into their own smem and signal the LEADER's full
+  // barrier; the leader's MMA lane issues M = 256 MMAs that read both CTAs' smem and write both CTAs' TMEM; its
+  // commits are multicast to both CTAs (smem slot free, accumulator ready); both epilogues drain their own TMEM and
+  // arrive on the leader's accumulator-free barrier. Shared-memory traffic per CTA drops by the half B tile, which
+  // is what bounds the single-CTA 128 x BN tile (profiles/r1_notes.md, finding 5).
   constexpr bool clustered = CLUSTER;  // compile-time: the default (unpaired) kernel carries none of this
   const uint32_t crank = clustered ? cluster_ctarank() : 0u;
   const int work_first = clustered ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -106,18 +111,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), clustered ? 2 : 1);  // a multicast slot is free when BOTH CTAs' MMAs have read it
+      mbar_init(full_bar(s), clustered ? 2 : 1);  // paired: leader's expect_tx arrive + peer's remote arrive
+      mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 8);
+      mbar_init(tempty_bar(i), clustered ? 16 : 8);  // paired: both CTAs' epilogue warps free the leader's accumulator
     }
     fence_mbar_init();
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  if (warp == 1) {
+    if (clustered) tmem_alloc2(smem_u32(tmem_ptr_smem), TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   if (clustered) cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive can reach them
@@ -146,20 +154,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           const uint32_t sA = smem_base + stage * stage_bytes;
           const uint32_t sB = sA + A_STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, stage_bytes);
-          if (a.conv) {
-            const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
+          if (clustered) {
+            // every byte of both CTAs is accounted on the leader's barrier
+            if (crank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
+            else mbar_arrive_remote(fb, 0u);
+            if (a.conv) {
+              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+              const int dy = tap / 3, dx = tap - dy * 3;
+              tma2_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
+            } else {
+              const int k0 = kb * BLOCK_K;
+              if (k0 < a.K1) tma2_load_2d(sA, &a.tmA, fb, k0, m0);
+              else tma2_load_2d(sA, &a.tmA2, fb, k0 - a.K1, m0);
+            }
+            tma2_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN + (int)crank * (BN >> 1));  // my half of B
           } else {
-            const int k0 = kb * BLOCK_K;
-            if (k0 < a.K1) tma_load_2d(sA, &a.tmA, fb, k0, m0);
-            else tma_load_2d(sA, &a.tmA2, fb, k0 - a.K1, m0);
-          }
-          if (clustered) {  // my half of the B tile, delivered to both CTAs
-            const int hb = BN >> 1;
-            tma_load_2d_mc(sB + crank * (uint32_t)hb * 128u, &a.tmB, fb, kb * BLOCK_K, n_blk * BN + (int)crank * hb, (uint16_t)3);
-          } else {
+            mbar_expect_tx(fb, stage_bytes);
+            if (a.conv) {
+              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+              const int dy = tap / 3, dx = tap - dy * 3;
+              tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
+            } else {
+              const int k0 = kb * BLOCK_K;
+              if (k0 < a.K1) tma_load_2d(sA, &a.tmA, fb, k0, m0);
+              else tma_load_2d(sA, &a.tmA2, fb, k0 - a.K1, m0);
+            }
             tma_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -168,8 +187,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BF16 ? 1 : 0, BLOCK_M, BN, 0, 0);
+    if (lane == 0 && (!clustered || crank == 0)) {  // paired: only the leader CTA issues
+      const uint32_t idesc = umma_idesc(BF16 ? 1 : 0, clustered ? 2 * BLOCK_M : BLOCK_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -188,13 +207,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // +32 bytes along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
-            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (clustered) tc2_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (clustered) tc_commit_mc(empty_bar(stage), (uint16_t)3);
+          if (clustered) tc2_commit_mc(empty_bar(stage), (uint16_t)3);  // both CTAs' slot `stage` is free
           else tc_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));
+        if (clustered) tc2_commit_mc(tfull_bar(acc), (uint16_t)3);      // both CTAs' accumulator halves are ready
+        else tc_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -338,7 +359,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (clustered && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);  // the leader's MMA lane owns the accumulators
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -349,7 +373,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   if (clustered) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (clustered) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -428,7 +453,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.BN % 16 != 0 || a.BN < 16 || a.BN > 256) { set_last_error(__FILE__, __LINE__, "gemm: bad BN"); return -1; }
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
-  const int stage_bytes = A_STAGE_BYTES + a.BN * 128;
+  const int stage_bytes = A_STAGE_BYTES + (a.cluster == 2 ? a.BN / 2 : a.BN) * 128;
   const size_t smem = (size_t)a.num_stages * stage_bytes + 8 * (2 * a.num_stages + 4) + 16 + SBIAS_BYTES + 1024;
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
   const int tiles = num_m * num_n;
@@ -464,13 +489,12 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   return 0;
 }
 
-// Pair CTAs (TMA multicast of the B tile) when the geometry allows it: halves the weight-tile L2 traffic per CTA.
-// Measured on B200 (profiles/r1_notes.md): no gain — the 128 x BN single-CTA tile is bound by shared-memory
-// bandwidth (TMA writes + SS-mode MMA reads of the same 36-48 KB per k-block), not by L2, and multicast still lands
-// the full B tile in both CTAs. Kept (validated, off by default; SDXE_CLUSTER=1) as the scaffold for cta_group::2.
+// Pair CTAs (cta_group::2, 256-row tile pairs) when the geometry allows it. History (profiles/r1_notes.md): plain TMA
+// multicast of the B tile across the pair gave 0 % — the single-CTA tile is bound by shared-memory bandwidth, and
+// multicast still lands the full B tile in both CTAs; splitting B across the pair's smem is what cta_group::2 buys.
 int gemm_pick_cluster(int M, int BN) {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 0; }
+  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 1; }
   if (!mode) return 1;
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   return (num_m % 2 == 0 && num_m >= 2 && BN % 16 == 0 && BN >= 32) ? 2 : 1;
