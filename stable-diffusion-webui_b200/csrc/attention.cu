@@ -82,17 +82,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
-    if (lane == 0) {
-      if (a.q_resident) {
+    // converged warp, elected issue (see gemm.cu)
+    {
+      if (a.q_resident && elect_one()) {
         mbar_expect_tx(q_full, a.dqk_slabs * SLAB_BYTES);
         for (int c = 0; c < a.dqk_slabs; ++c) tma_load_3d(sQ + c * SLAB_BYTES, &a.tmQ, q_full, c * 64, q0, bh);
       }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
       auto push = [&](const CUtensorMap* tm, int c0, int r0) {
         mbar_wait(slot_empty(slot), phase ^ 1u);
-        mbar_expect_tx(slot_full(slot), SLAB_BYTES);
-        tma_load_3d(sRing + slot * SLAB_BYTES, tm, slot_full(slot), c0, r0, bh);
+        if (elect_one()) {
+          mbar_expect_tx(slot_full(slot), SLAB_BYTES);
+          tma_load_3d(sRing + slot * SLAB_BYTES, tm, slot_full(slot), c0, r0, bh);
+        }
+        __syncwarp();
         if (++slot == NS) { slot = 0; phase ^= 1u; }
       };
       for (int i = 0; i <= nblk; ++i) {
@@ -107,8 +112,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (converged warp, elected issue)
+    {
       const uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, 128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc(BF16 ? 1 : 0, 128, 64, 0, 1);
       // zero-padded tails are skipped: fewer K steps on the last Q/K slab, narrower N on the last V slab
@@ -121,10 +126,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         mbar_wait(slot_full(slot), phase);
         return sRing + slot * SLAB_BYTES;
       };
-      auto release = [&]() {  // slab is freed when the MMAs issued so far complete
+      auto release = [&]() {  // slab is freed when the MMAs issued so far complete (caller is the elected lane)
         tc_commit(slot_empty(slot));
-        if (++slot == NS) { slot = 0; phase ^= 1u; }
       };
+      auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1u; } };
       if (a.q_resident) mbar_wait(q_full, 0);
       for (int i = 0; i <= nblk; ++i) {
         if (i < nblk) {
@@ -144,13 +149,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
             const uint64_t kd = umma_desc_sw128(k_addr, 16, 1024);
             const int ks = (c == a.dqk_slabs - 1) ? ksteps_last : 4;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ks) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
-            if (q_slot_held) { tc_commit(slot_empty(q_slot)); (void)q_phase; }
-            release();
+              for (int k = 0; k < 4; ++k)
+                if (k < ks) tc_mma_f16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+              if (q_slot_held) tc_commit(slot_empty(q_slot));
+              release();
+              if (c == a.dqk_slabs - 1) tc_commit(s_full(i & 1));
+            }
+            __syncwarp();
+            (void)q_phase;
+            advance();
           }
-          tc_commit(s_full(i & 1));
         }
         if (i >= 1) {
           const int j = i - 1;  // O += P_j V_j
@@ -164,12 +174,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             const uint32_t d_o = tmem_base + TM_O + (uint32_t)(vs * 64);
             const uint64_t vd = umma_desc_sw128(v_addr, SLAB_BYTES, 1024);
             const uint32_t id = (vs == a.dv_slabs - 1) ? idesc_pv_last : idesc_pv;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // +16 key rows: +128 in V's addr>>4 field, +2 in P's
-              tc_mma_f16(d_o, (k < 4 ? pd0 : pd1) + 2 * (k & 3), vd + 128 * k, id, (j | k) != 0 ? 1u : 0u);
-            release();
+              for (int k = 0; k < 8; ++k)  // +16 key rows: +128 in V's addr>>4 field, +2 in P's
+                tc_mma_f16(d_o, (k < 4 ? pd0 : pd1) + 2 * (k & 3), vd + 128 * k, id, (j | k) != 0 ? 1u : 0u);
+              release();
+              if (vs == a.dv_slabs - 1) tc_commit(pv_done(j & 1));
+            }
+            __syncwarp();
+            advance();
           }
-          tc_commit(pv_done(j & 1));
         }
       }
     }

@@ -68,16 +68,24 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * QS * SLAB2);
-      for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < QS; ++c) tma_load_3d(sQ + (t * QS + c) * SLAB2, &a.tmQ, q_full, c * 64, q0 + t * 128, bh);
+    // converged warp, elected issue (see gemm.cu: issuing from a divergent single-lane region costs an ELECT/BRA.U.ANY
+    // loop per uniform-datapath instruction)
+    {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * QS * SLAB2);
+        for (int t = 0; t < 2; ++t)
+          for (int c = 0; c < QS; ++c) tma_load_3d(sQ + (t * QS + c) * SLAB2, &a.tmQ, q_full, c * 64, q0 + t * 128, bh);
+      }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
       auto push = [&](const CUtensorMap* tm, int c0, int r0) {
         mbar_wait(slot_empty(slot), phase ^ 1u);
-        mbar_expect_tx(slot_full(slot), SLAB2);
-        tma_load_3d(sRing + slot * SLAB2, tm, slot_full(slot), c0, r0, bh);
+        if (elect_one()) {
+          mbar_expect_tx(slot_full(slot), SLAB2);
+          tma_load_3d(sRing + slot * SLAB2, tm, slot_full(slot), c0, r0, bh);
+        }
+        __syncwarp();
         if (++slot == NS) { slot = 0; phase ^= 1u; }
       };
       // ring order == consumption order: K_0, (K_1, V_0), (K_2, V_1), ..., V_{n-1}
@@ -89,8 +97,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (converged warp, elected issue)
+    {
       const uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, 128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc(BF16 ? 1 : 0, 128, 64, 0, 1);
       const int ksteps_last = (a.dqk - (QS - 1) * 64 + 15) / 16;
@@ -122,29 +130,43 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       int k_slot[2] = {0, 0}, v_slot[2] = {0, 0};
       auto issue_s = [&](int t) {
         const uint32_t d_s = tmem_base + (uint32_t)(t * 128);
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < QS) {
-            const int ks = (c == QS - 1) ? ksteps_last : 4;
+          for (int c = 0; c < 2; ++c) {
+            if (c < QS) {
+              const int ks = (c == QS - 1) ? ksteps_last : 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ks) tc_mma_f16(d_s, qd[t][c] + 2 * k, kd[c] + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                if (k < ks) tc_mma_f16(d_s, qd[t][c] + 2 * k, kd[c] + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+            }
           }
+          tc_commit(s_full(t));
         }
-        tc_commit(s_full(t));
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int j) {
+        if (elect_one()) {
 #pragma unroll
-        for (int vs = 0; vs < 2; ++vs) {
-          if (vs < VS) {
-            const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
-            const uint32_t id = (vs == VS - 1) ? idesc_pv_last : idesc_pv;
+          for (int vs = 0; vs < 2; ++vs) {
+            if (vs < VS) {
+              const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
+              const uint32_t id = (vs == VS - 1) ? idesc_pv_last : idesc_pv;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // 16 key rows per step: +2048 B in V (= +128 in the addr>>4 field), +32 B in P
-              tc_mma_f16(d_o, pd[t][k >> 2] + 2 * (k & 3), vd[vs] + 128 * k, id, (j | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 8; ++k)  // 16 key rows per step: +2048 B in V (= +128 in the addr>>4 field), +32 B in P
+                tc_mma_f16(d_o, pd[t][k >> 2] + 2 * (k & 3), vd[vs] + 128 * k, id, (j | k) != 0 ? 1u : 0u);
+            }
           }
+          tc_commit(pv_done(t));
         }
-        tc_commit(pv_done(t));
+        __syncwarp();
+      };
+      auto release = [&](const int* slots, int n) {  // free ring slabs once the MMAs issued so far have read them
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < n) tc_commit(slot_empty(slots[c]));
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
 #pragma unroll
@@ -153,9 +175,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       tc_fence_after();
       issue_s(0);
       issue_s(1);
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-        if (c < QS) tc_commit(slot_empty(k_slot[c]));
+      release(k_slot, QS);
       for (int i = 0; i < nblk; ++i) {
         const bool more = i + 1 < nblk;
         if (more) {
@@ -173,14 +193,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
           if (more) issue_s(t);
           issue_pv(t, i);
         }
-        if (more) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-            if (c < QS) tc_commit(slot_empty(k_slot[c]));
-        }
-#pragma unroll
-        for (int vs = 0; vs < 2; ++vs)
-          if (vs < VS) tc_commit(slot_empty(v_slot[vs]));
+        if (more) release(k_slot, QS);
+        release(v_slot, VS);
       }
     }
   } else {

@@ -132,25 +132,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Producer and MMA warps run their loops CONVERGED (all 32 lanes wait on the barriers) and only the asynchronous
+  // issue itself is predicated on one elected lane. Issuing from inside a divergent `if (lane == 0)` region makes the
+  // compiler wrap every uniform-datapath instruction (UTMALDG / UTCHMMA / UTCBAR) in an ELECT + BRA.U.ANY loop with
+  // R2UR conversions: ~70 dependent instructions (~700 cycles) per k-block on the single lane that feeds the tensor
+  // pipe — measured as the limiter of every tile narrower than 256 (tensor pipe 50 % busy at BN = 160).
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = work_first; tile < num_tiles; tile += work_step) {
-        const int n_blk = tile % num_n;
-        const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
-        const int m0 = m_blk * BLOCK_M;
-        int img0 = 0, h0 = 0, w0 = 0;
-        if (a.conv) {
-          const int hw = a.H * a.W;
-          img0 = m0 / hw;
-          const int rem = m0 - img0 * hw;
-          h0 = rem / a.W;
-          w0 = rem - h0 * a.W;
-        }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = work_first; tile < num_tiles; tile += work_step) {
+      const int n_blk = tile % num_n;
+      const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
+      const int m0 = m_blk * BLOCK_M;
+      int img0 = 0, h0 = 0, w0 = 0;
+      if (a.conv) {
+        const int hw = a.H * a.W;
+        img0 = m0 / hw;
+        const int rem = m0 - img0 * hw;
+        h0 = rem / a.W;
+        w0 = rem - h0 * a.W;
+      }
+      int tap = 0, cb = 0;  // conv: k-block -> (tap, channel block) without divisions
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
           const uint32_t sA = smem_base + stage * stage_bytes;
           const uint32_t sB = sA + A_STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
@@ -159,7 +165,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             if (crank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
             else mbar_arrive_remote(fb, 0u);
             if (a.conv) {
-              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
               const int dy = tap / 3, dx = tap - dy * 3;
               tma2_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
             } else {
@@ -171,7 +176,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           } else {
             mbar_expect_tx(fb, stage_bytes);
             if (a.conv) {
-              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
               const int dy = tap / 3, dx = tap - dy * 3;
               tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
             } else {
@@ -181,14 +185,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             }
             tma_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN);
           }
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++cb == a.cblocks) { cb = 0; ++tap; }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!clustered || crank == 0)) {  // paired: only the leader CTA issues
+    if (!clustered || crank == 0) {  // paired: only the leader CTA issues
       const uint32_t idesc = umma_idesc(BF16 ? 1 : 0, clustered ? 2 * BLOCK_M : BLOCK_M, BN, 0, 0);
+      // descriptors of stage 0; stage s adds s * stage_bytes to the (address >> 4) field
+      const uint64_t adesc0 = umma_desc_sw128(smem_base, 16, 1024);
+      const uint64_t bdesc0 = umma_desc_sw128(smem_base + A_STAGE_BYTES, 16, 1024);
+      const uint32_t stage_inc = stage_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -200,22 +210,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * stage_bytes;
-          const uint32_t sB = sA + A_STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sB, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
+          if (elect_one()) {
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * stage_inc);
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * stage_inc);
             // +32 bytes along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
-            if (clustered) tc2_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (clustered) {
+              tc2_mma_f16(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+              tc2_mma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              tc2_mma_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              tc2_mma_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              tc2_commit_mc(empty_bar(stage), (uint16_t)3);  // both CTAs' slot `stage` is free
+            } else {
+              tc_mma_f16(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+              tc_mma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              tc_mma_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              tc_mma_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              tc_commit(empty_bar(stage));
+            }
           }
-          if (clustered) tc2_commit_mc(empty_bar(stage), (uint16_t)3);  // both CTAs' slot `stage` is free
-          else tc_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        if (clustered) tc2_commit_mc(tfull_bar(acc), (uint16_t)3);      // both CTAs' accumulator halves are ready
-        else tc_commit(tfull_bar(acc));
+        if (elect_one()) {
+          if (clustered) tc2_commit_mc(tfull_bar(acc), (uint16_t)3);  // both CTAs' accumulator halves are ready
+          else tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -494,7 +514,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
 // multicast still lands the full B tile in both CTAs; splitting B across the pair's smem is what cta_group::2 buys.
 int gemm_pick_cluster(int M, int BN) {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 1; }
+  if (mode < 0) { const char* e = getenv("SDXE_CLUSTER"); mode = e ? atoi(e) : 0; }
   if (!mode) return 1;
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   return (num_m % 2 == 0 && num_m >= 2 && BN % 16 == 0 && BN >= 32) ? 2 : 1;
