@@ -5,8 +5,9 @@
 // one kernel for UNet self-attention (Nk = Nq in {4096,1024,256,64}), cross-attention (Nk = 77*k) and the
 // VAE AttnBlock (single head, d = 512, run as two passes over 256-wide halves of V).
 //
-// Inputs are per-head padded tensors [B*H, tokens, dpad] (dpad multiple of 64, pad columns zero) written by
-// the q/k/v projection GEMM's EPI_HEADS epilogue; output is merged-head [B*Nq, H*d] for the out-projection.
+// Inputs are the projection GEMMs' row-major outputs ([B*tokens, 3C] = q|k|v, heads contiguous inside each) seen
+// through 4D tensor maps (d, token, head, batch): a 64-wide slab reaching past the head dim d is zero-filled by TMA,
+// so no padded / transposed per-head copy exists. Output is merged-head [B*Nq, H*d] for the out-projection.
 //
 // CTA = one 128-row query tile of one (batch, head):
 //   warp 0    : TMA producer. Q slabs once (or streamed when d = 512), then K_i / V_i slabs (128 x 64 elements,
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
   const int bh = blockIdx.y;
+  const int hb_b = bh / a.H, hb_h = bh - hb_b * a.H;  // (batch, head) coordinates of the 4D per-head tensor maps
   const int nblk = (a.Nk + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     {
       if (a.q_resident && elect_one()) {
         mbar_expect_tx(q_full, a.dqk_slabs * SLAB_BYTES);
-        for (int c = 0; c < a.dqk_slabs; ++c) tma_load_3d(sQ + c * SLAB_BYTES, &a.tmQ, q_full, c * 64, q0, bh);
+        for (int c = 0; c < a.dqk_slabs; ++c) tma_load_4d(sQ + c * SLAB_BYTES, &a.tmQ, q_full, c * 64, q0, hb_h, hb_b);
       }
       __syncwarp();
       int slot = 0;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         mbar_wait(slot_empty(slot), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(slot_full(slot), SLAB_BYTES);
-          tma_load_3d(sRing + slot * SLAB_BYTES, tm, slot_full(slot), c0, r0, bh);
+          tma_load_4d(sRing + slot * SLAB_BYTES, tm, slot_full(slot), c0, r0, hb_h, hb_b);
         }
         __syncwarp();
         if (++slot == NS) { slot = 0; phase ^= 1u; }

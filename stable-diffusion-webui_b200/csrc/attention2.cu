@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int bh = blockIdx.y;
+  const int hb_b = bh / a.H, hb_h = bh - hb_b * a.H;  // (batch, head) coordinates of the 4D per-head tensor maps
   const int nblk = (a.Nk + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       if (elect_one()) {
         mbar_expect_tx(q_full, 2 * QS * SLAB2);
         for (int t = 0; t < 2; ++t)
-          for (int c = 0; c < QS; ++c) tma_load_3d(sQ + (t * QS + c) * SLAB2, &a.tmQ, q_full, c * 64, q0 + t * 128, bh);
+          for (int c = 0; c < QS; ++c) tma_load_4d(sQ + (t * QS + c) * SLAB2, &a.tmQ, q_full, c * 64, q0 + t * 128, hb_h, hb_b);
       }
       __syncwarp();
       int slot = 0;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         mbar_wait(slot_empty(slot), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(slot_full(slot), SLAB2);
-          tma_load_3d(sRing + slot * SLAB2, tm, slot_full(slot), c0, r0, bh);
+          tma_load_4d(sRing + slot * SLAB2, tm, slot_full(slot), c0, r0, hb_h, hb_b);
         }
         __syncwarp();
         if (++slot == NS) { slot = 0; phase ^= 1u; }

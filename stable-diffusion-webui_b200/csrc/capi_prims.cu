@@ -23,27 +23,17 @@ int sdxe_attention(const void* q, const void* k, const void* v, void* out, int B
   if (!is16(dtype) || D % 8 != 0 || D > 512 || D <= 0) { set_last_error(__FILE__, __LINE__, "sdxe_attention: dtype/D"); return -2; }
   const bool bf16 = dtype == SDXE_BF16;
   const int Dpad = (D + 63) / 64 * 64;
-  const void *qp = q, *kp = k, *vp = v;
-  void* scratch = nullptr;
-  if (Dpad != D) {
-    const size_t nq = (size_t)B * H * Nq * Dpad, nk = (size_t)B * H * Nk * Dpad;
-    SDXE_CUDA_CHECK(cudaMallocAsync(&scratch, (nq + 2 * nk) * 2, stream));
-    uint16_t* s = (uint16_t*)scratch;
-    if (pad_heads_launch(q, s, (int64_t)B * H * Nq, D, Dpad, stream)) return -1;
-    if (pad_heads_launch(k, s + nq, (int64_t)B * H * Nk, D, Dpad, stream)) return -1;
-    if (pad_heads_launch(v, s + nq + nk, (int64_t)B * H * Nk, D, Dpad, stream)) return -1;
-    qp = s; kp = s + nq; vp = s + nq + nk;
-  }
   // value dim is processed in passes of at most 256 columns (TMEM: 2 x 128 S columns + 256 O columns)
   int rc = 0;
   for (int v0 = 0; v0 < D && rc == 0; v0 += 256) {
     const int dv = std::min(256, D - v0);
     AttnArgs a;
     memset(&a, 0, sizeof(a));
-    if (make_tmap_3d(&a.tmQ, qp, Dpad, Nq, (int64_t)B * H, Dpad, (int64_t)Nq * Dpad, 128)) return -1;
-    if (make_tmap_3d(&a.tmK, kp, Dpad, Nk, (int64_t)B * H, Dpad, (int64_t)Nk * Dpad, 128)) return -1;
+    // [B, H, N, D] contiguous seen as (d, token, head, batch); boxes reaching past D are zero-filled by TMA
+    if (make_tmap_heads(&a.tmQ, q, D, Nq, H, B, D, (int64_t)Nq * D, (int64_t)H * Nq * D, 128)) return -1;
+    if (make_tmap_heads(&a.tmK, k, D, Nk, H, B, D, (int64_t)Nk * D, (int64_t)H * Nk * D, 128)) return -1;
     const int dvpad = (dv + 63) / 64 * 64;
-    if (make_tmap_3d(&a.tmV, (const uint16_t*)vp + v0, std::min(dvpad, Dpad - v0), Nk, (int64_t)B * H, Dpad, (int64_t)Nk * Dpad, 128)) return -1;
+    if (make_tmap_heads(&a.tmV, (const uint16_t*)v + v0, dv, Nk, H, B, D, (int64_t)Nk * D, (int64_t)H * Nk * D, 128)) return -1;
     a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk;
     a.dqk_slabs = Dpad / 64;
     a.dv_slabs = dvpad / 64;
@@ -58,7 +48,6 @@ int sdxe_attention(const void* q, const void* k, const void* v, void* out, int B
     rc = attention_launch(a, bf16, stream);
     count_launch();
   }
-  if (scratch) cudaFreeAsync(scratch, stream);
   return rc;
 }
 
@@ -88,18 +77,15 @@ int sdxe_gemm(const void* A, const void* W, void* out, int M, int N, int K, cons
       bp = b2;
     }
   }
-  a.num_stages = gemm_pick_stages(a.BN);
   if (make_tmap_2d(&a.tmA, A, M, K, K, 128)) return -1;
   a.tmA2 = a.tmA;
-  a.cluster = gemm_pick_cluster(a.M, a.BN);
-    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
-  if (make_tmap_2d(&a.tmB, Wp, N, K, K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bp;
   a.residual = residual;
   a.ldr = N;
   a.out = out;
   a.ldo = geglu ? N / 2 : N;
   a.rows_per_sample = 1;
+  if (gemm_finish_args(a, Wp, N, K)) return -1;
   int rc = gemm_launch(a, bf16, stream);
   count_launch();
   if (scratch) cudaFreeAsync(scratch, stream);
@@ -119,16 +105,13 @@ int sdxe_conv3x3_nhwc(const void* x, const void* w, void* out, int n, int h, int
   a.conv = 1; a.cblocks = cin / 64; a.H = h; a.W = wd; a.bh = bh; a.bn = bn;
   a.epi = EPI_PLAIN;
   a.BN = gemm_pick_bn(a.M, a.N, a.K, a.epi);
-  a.num_stages = gemm_pick_stages(a.BN);
   if (make_tmap_nhwc(&a.tmA, x, n, h, wd, cin, bw, bh, bn)) return -1;
   a.tmA2 = a.tmA;
-  a.cluster = gemm_pick_cluster(a.M, a.BN);
-    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
-  if (make_tmap_2d(&a.tmB, w, cout, a.K, a.K, a.cluster == 2 ? a.BN / 2 : a.BN)) return -1;
   a.bias = bias;
   a.out = out;
   a.ldo = cout;
   a.rows_per_sample = 1;
+  if (gemm_finish_args(a, w, cout, a.K)) return -1;
   int rc = gemm_launch(a, bf16, stream);
   count_launch();
   return rc;

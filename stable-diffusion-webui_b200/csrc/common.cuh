@@ -104,6 +104,16 @@ SDXE_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, i
       : "memory");
 }
 
+// TMA store smem -> global (bulk async-group completion). The issuing thread commits and later waits on its own groups.
+SDXE_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+SDXE_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SDXE_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
+SDXE_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }            // writes done
+
 // multicast variant: the box lands at the same smem offset in every CTA of `mask`, each CTA's mbarrier (same offset)
 // receives the complete_tx for the bytes written into it
 SDXE_DEVINL void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
@@ -340,6 +350,12 @@ const char* last_error();
 
 // 16-bit row-major 2D [rows, cols] with row pitch ld (elements): box = 64 cols x box_rows, 128B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+// same with an explicit box; swizzle = the box's row bytes (32 / 64 / 128 B) — the GEMM epilogue's store / residual boxes
+int make_tmap_2d_box(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
+// per-head view of a row-major activation: element (j, tok, h, b) at base + b*batch_stride + tok*tok_stride + h*head_stride
+// + j (strides in elements, multiples of 8). Inner extent d (NOT padded): a 64-wide box past d is zero-filled by TMA.
+int make_tmap_heads(CUtensorMap* out, const void* base, int64_t d, int64_t tokens, int64_t heads, int64_t batch,
+                    int64_t tok_stride, int64_t head_stride, int64_t batch_stride, int box_rows);
 // 16-bit 3D [d2, d1 rows, d0 cols] with pitches: box = 64 x box_rows x 1.
 int make_tmap_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t pitch1, int64_t pitch2,
                  int box_rows);

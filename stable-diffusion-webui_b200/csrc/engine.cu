@@ -143,7 +143,6 @@ struct sdxe_engine {
 
   // activation pool
   std::multimap<size_t, void*> free_list;
-  std::map<std::string, std::vector<void*>> head_pool;  // zero-padded per-head q/k/v buffers by geometry
   std::vector<void*> all_allocs;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   cudaStream_t cap_stream = nullptr;
@@ -169,8 +168,6 @@ struct sdxe_engine {
   // --- activations
   Buf alloc(size_t bytes);
   void release(Buf& b);
-  void* alloc_heads(int bh, int tokens, int d, int dpad, const char* tag);
-  void release_heads(void* p, int bh, int tokens, int d, int dpad, const char* tag);
 };
 
 namespace {
@@ -236,8 +233,6 @@ struct Builder {
     const void* residual = nullptr;
     int ldr = 0;
     int epi = EPI_PLAIN;
-    int heads = 0, head_dim = 0, head_pad = 0, tokens = 0;
-    void* outs[3] = {nullptr, nullptr, nullptr};
     int ldo = 0;
   };
   int gemm(const void* A, int lda, int64_t M, const LinW& W, void* out, const GemmOpt& o) {
@@ -247,20 +242,15 @@ struct Builder {
     a.K1 = o.A2 ? o.K1 : W.K;
     a.epi = o.epi;
     a.BN = (o.epi == EPI_GEGLU) ? W.geglu_tile : gemm_pick_bn(a.M, a.N, a.K, a.epi);
-    a.num_stages = gemm_pick_stages(a.BN);
     ECHK(make_tmap_2d(&a.tmA, A, M, a.K1, lda, 128));
     if (o.A2) ECHK(make_tmap_2d(&a.tmA2, o.A2, M, W.K - o.K1, W.K - o.K1, 128));
     else a.tmA2 = a.tmA;
-    a.cluster = gemm_pick_cluster(a.M, a.BN);
-    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
-    ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), W.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
     a.bias = W.b;
     a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
     a.residual = o.residual; a.ldr = o.ldr;
     a.out = out;
-    a.ldo = o.ldo ? o.ldo : (o.epi == EPI_GEGLU ? W.N / 2 : W.N);
-    a.heads = o.heads; a.head_dim = o.head_dim; a.head_pad = o.head_pad; a.tokens = o.tokens;
-    for (int i = 0; i < 3; ++i) a.outs[i] = o.outs[i];
+    a.ldo = o.ldo ? o.ldo : (o.epi == EPI_GEGLU ? W.N / 2 : (W.N + 7) / 8 * 8);
+    ECHK(gemm_finish_args(a, W.w, std::max(W.N, W.Nrows), W.ld));
     const bool b = bf16;
     const double nout = (o.epi == EPI_GEGLU) ? W.N / 2.0 : (double)W.N;
     const double by = 2.0 * ((double)M * W.K + (double)W.N * W.K + (double)M * nout + (o.residual ? (double)M * nout : 0.0));
@@ -282,16 +272,13 @@ struct Builder {
       a.conv = 1; a.cblocks = x.c / 64; a.H = x.h; a.W = x.w; a.bh = bh; a.bn = bn;
       a.epi = EPI_PLAIN;
       a.BN = gemm_pick_bn(a.M, a.N, a.K, a.epi);
-      a.num_stages = gemm_pick_stages(a.BN);
       ECHK(make_tmap_nhwc(&a.tmA, x.p, x.n, x.h, x.w, x.c, bw, bh, bn));
       a.tmA2 = a.tmA;
-      a.cluster = gemm_pick_cluster(a.M, a.BN);
-    a.num_stages = gemm_pick_stages(a.cluster == 2 ? a.BN / 2 : a.BN);
-      ECHK(make_tmap_2d(&a.tmB, W.w, std::max(W.N, W.Nrows), a.K, W.ld, a.cluster == 2 ? a.BN / 2 : a.BN));
       a.bias = W.b;
       a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
       a.residual = o.residual; a.ldr = o.ldr;
       a.out = out; a.ldo = ldo;
+      ECHK(gemm_finish_args(a, W.w, std::max(W.N, W.Nrows), W.ld));
       const bool b = bf16;
       const double Md = (double)a.M;
       const double by = 2.0 * (Md * x.c + (double)W.N * a.K + Md * W.N + (o.residual ? Md * W.N : 0.0));
@@ -347,17 +334,21 @@ struct Builder {
                          4.0 * (double)rows * C, "ln rows=" + std::to_string(rows) + " C=" + std::to_string(C)));
     return 0;
   }
-  int attention(const void* q, const void* k, const void* v, int B, int H, int Nq, int Nk, int d, int dpad, int ldq,
-                int ldkv, int64_t q_bstride, int64_t kv_bstride, float scale, void* out, int ldo, int dv_total) {
+  // q: [B*Nq, ldq], k / v: [B*Nk, ldkv] row-major activations whose columns h*d .. h*d+d-1 belong to head h (the
+  // projection GEMM's natural output). The kernels see them through 4D tensor maps (d, token, head, batch); a 64-wide
+  // box reaching past d is zero-filled by TMA, so no padded per-head copy exists.
+  int attention(const void* q, const void* k, const void* v, int B, int H, int Nq, int Nk, int d, int ldq, int ldkv,
+                float scale, void* out, int ldo, int dv_total) {
+    const int dpad = (d + 63) / 64 * 64;
     // dv_total > 256 (VAE, d = 512): passes over 256-wide slices of V
     for (int v0 = 0; v0 < dv_total; v0 += 256) {
       const int dv = std::min(256, dv_total - v0);
       const int dvpad = (dv + 63) / 64 * 64;
       AttnArgs a;
       memset(&a, 0, sizeof(a));
-      ECHK(make_tmap_3d(&a.tmQ, q, dpad, Nq, (int64_t)B * H, ldq, q_bstride, 128));
-      ECHK(make_tmap_3d(&a.tmK, k, dpad, Nk, (int64_t)B * H, ldkv, kv_bstride, 128));
-      ECHK(make_tmap_3d(&a.tmV, (const uint16_t*)v + v0, std::min(dvpad, dpad - v0), Nk, (int64_t)B * H, ldkv, kv_bstride, 128));
+      ECHK(make_tmap_heads(&a.tmQ, q, d, Nq, H, B, ldq, d, (int64_t)Nq * ldq, 128));
+      ECHK(make_tmap_heads(&a.tmK, k, d, Nk, H, B, ldkv, d, (int64_t)Nk * ldkv, 128));
+      ECHK(make_tmap_heads(&a.tmV, (const uint16_t*)v + v0, dv, Nk, H, B, ldkv, d, (int64_t)Nk * ldkv, 128));
       a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk;
       a.dqk_slabs = dpad / 64;
       a.dv_slabs = dvpad / 64;
@@ -411,7 +402,7 @@ struct Builder {
 
   // SpatialTransformer (modules/sd_hijack_unet.py:83-102) with BasicTransformerBlocks
   int spatial_transformer(const STW& st, Act& x, const void* ctx16, int ctx_len, int ctx_dim, Act& out) {
-    const int C = st.C, H = st.heads, dh = st.dh, dpad = (dh + 63) / 64 * 64;
+    const int C = st.C, H = st.heads, dh = st.dh;
     const int64_t M = x.rows();
     const int tokens = x.h * x.w, B = x.n;
     const float scale = 1.0f / sqrtf((float)dh);
@@ -424,18 +415,12 @@ struct Builder {
       // --- self attention
       Act ln = new_act(x.n, x.h, x.w, C);
       ECHK(layer_norm(h.p, M, tb.ln1, ln.p));
-      void* q = e->alloc_heads(B * H, tokens, dh, dpad, "q");
-      void* k = e->alloc_heads(B * H, tokens, dh, dpad, "k");
-      void* v = e->alloc_heads(B * H, tokens, dh, dpad, "v");
-      GemmOpt oq;
-      oq.epi = EPI_HEADS; oq.heads = H; oq.head_dim = dh; oq.head_pad = dpad; oq.tokens = tokens;
-      oq.outs[0] = q; oq.outs[1] = k; oq.outs[2] = v;
-      ECHK(gemm(ln.p, C, M, tb.qkv1, nullptr, oq));
+      Act qkv = new_act(x.n, x.h, x.w, 3 * C);
+      ECHK(gemm(ln.p, C, M, tb.qkv1, qkv.p, GemmOpt()));  // columns: [q | k | v], heads contiguous inside each
       Act att = new_act(x.n, x.h, x.w, C);
-      ECHK(attention(q, k, v, B, H, tokens, tokens, dh, dpad, dpad, dpad, (int64_t)tokens * dpad, (int64_t)tokens * dpad, scale,
-                     att.p, C, dh));
-      e->release_heads(k, B * H, tokens, dh, dpad, "k");
-      e->release_heads(v, B * H, tokens, dh, dpad, "v");
+      const uint16_t* qkv16 = (const uint16_t*)qkv.p;
+      ECHK(attention(qkv16, qkv16 + C, qkv16 + 2 * C, B, H, tokens, tokens, dh, 3 * C, 3 * C, scale, att.p, C, dh));
+      free_act(qkv);
       Act h2 = new_act(x.n, x.h, x.w, C);
       GemmOpt oo;
       oo.residual = h.p; oo.ldr = C;
@@ -444,21 +429,13 @@ struct Builder {
       h = h2;
       // --- cross attention
       ECHK(layer_norm(h.p, M, tb.ln2, ln.p));
-      GemmOpt oq2;
-      oq2.epi = EPI_HEADS; oq2.heads = H; oq2.head_dim = dh; oq2.head_pad = dpad; oq2.tokens = tokens;
-      oq2.outs[0] = q;
-      ECHK(gemm(ln.p, C, M, tb.q2, nullptr, oq2));
-      void* k2 = e->alloc_heads(B * H, ctx_len, dh, dpad, "k");
-      void* v2 = e->alloc_heads(B * H, ctx_len, dh, dpad, "v");
-      GemmOpt okv;
-      okv.epi = EPI_HEADS; okv.heads = H; okv.head_dim = dh; okv.head_pad = dpad; okv.tokens = ctx_len;
-      okv.outs[0] = k2; okv.outs[1] = v2;
-      ECHK(gemm(ctx16, ctx_dim, (int64_t)B * ctx_len, tb.kv2, nullptr, okv));
-      ECHK(attention(q, k2, v2, B, H, tokens, ctx_len, dh, dpad, dpad, dpad, (int64_t)tokens * dpad, (int64_t)ctx_len * dpad,
-                     scale, att.p, C, dh));
-      e->release_heads(q, B * H, tokens, dh, dpad, "q");
-      e->release_heads(k2, B * H, ctx_len, dh, dpad, "k");
-      e->release_heads(v2, B * H, ctx_len, dh, dpad, "v");
+      Act q2 = new_act(x.n, x.h, x.w, C);
+      ECHK(gemm(ln.p, C, M, tb.q2, q2.p, GemmOpt()));
+      Act kv2 = new_act(B, 1, ctx_len, 2 * C);  // columns: [k | v]
+      ECHK(gemm(ctx16, ctx_dim, (int64_t)B * ctx_len, tb.kv2, kv2.p, GemmOpt()));
+      ECHK(attention(q2.p, kv2.p, (const uint16_t*)kv2.p + C, B, H, tokens, ctx_len, dh, C, 2 * C, scale, att.p, C, dh));
+      free_act(q2);
+      free_act(kv2);
       Act h3 = new_act(x.n, x.h, x.w, C);
       GemmOpt oo2;
       oo2.residual = h.p; oo2.ldr = C;
@@ -818,23 +795,6 @@ void sdxe_engine::release(Buf& b) {
   if (b.p) free_list.insert({b.bytes, b.p});
   b.p = nullptr;
 }
-static std::string head_key(int bh, int tokens, int d, int dpad, const char* tag) {
-  return std::string(tag) + ":" + std::to_string(bh) + ":" + std::to_string(tokens) + ":" + std::to_string(d) + ":" + std::to_string(dpad);
-}
-void* sdxe_engine::alloc_heads(int bh, int tokens, int d, int dpad, const char* tag) {
-  auto& v = head_pool[head_key(bh, tokens, d, dpad, tag)];
-  if (!v.empty()) { void* p = v.back(); v.pop_back(); return p; }
-  void* p = nullptr;
-  const size_t bytes = (size_t)bh * tokens * dpad * 2;
-  if (cudaMalloc(&p, bytes) != cudaSuccess) { set_last_error(__FILE__, __LINE__, "cudaMalloc failed (head pool)"); return nullptr; }
-  cudaMemset(p, 0, bytes);  // pad columns stay zero forever: only the first d columns of a row are ever written
-  all_allocs.push_back(p);
-  return p;
-}
-void sdxe_engine::release_heads(void* p, int bh, int tokens, int d, int dpad, const char* tag) {
-  head_pool[head_key(bh, tokens, d, dpad, tag)].push_back(p);
-}
-
 // =================================================================================================================
 // plans
 // =================================================================================================================
@@ -1116,8 +1076,7 @@ int build_vae_plan(sdxe_engine* e, Plan* p, int n, int h, int w) {
     if (dpad != C || C > 512) EFAIL("vae attention: channel count must be a multiple of 64 and <= 512");
     Act att = B.new_act(n, cur.h, cur.w, C);
     const uint16_t* qp = (const uint16_t*)qkv.p;
-    ECHK(B.attention(qp, qp + C, qp + 2 * C, n, 1, tokens, tokens, C, dpad, 3 * C, 3 * C, (int64_t)tokens * 3 * C,
-                     (int64_t)tokens * 3 * C, 1.0f / sqrtf((float)C), att.p, C, C));
+    ECHK(B.attention(qp, qp + C, qp + 2 * C, n, 1, tokens, tokens, C, 3 * C, 3 * C, 1.0f / sqrtf((float)C), att.p, C, C));
     e->release(qkv);
     Act o = B.new_act(n, cur.h, cur.w, C);
     Builder::GemmOpt op;

@@ -1,12 +1,11 @@
 // tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
 //
-//   out[M, N] = A[M, K] * W[N, K]^T  (+ bias + per-sample vector + residual | GEGLU | head scatter)
+//   out[M, N] = A[M, K] * W[N, K]^T  (+ bias + per-sample vector + residual | GEGLU)
 //
 // Replaces, on the UNet / VAE hot path of the reference (all PyTorch library dispatch there):
 //   * ResBlock / Upsample / VAE conv3x3      (ldm openaimodel.py ResBlock) -> conv mode
 //   * conv1x1 proj_in/proj_out/skip, Linear q/k/v/out/FF                          -> plain mode
 //   * GEGLU (ldm attention.py GEGLU: x * gelu(gate))                                         -> EPI_GEGLU
-//   * the q/k/v head split of sd_hijack_optimizations.py:525-527                              -> EPI_HEADS
 //
 // Structure (one CTA per SM, persistent over output tiles of 128 x BN):
 //   warp 0   : TMA producer. A tile = 128 rows x 64 K (16 KB, 128B swizzle). In conv mode the A tile is a
@@ -14,8 +13,9 @@
 //              zero fill IS the convolution padding, so no im2col buffer ever exists.
 //   warp 1   : tcgen05.mma issuer (single thread), fp32 accumulators in TMEM, double buffered (2 x BN columns)
 //   warps 2-9: epilogue (two warps per TMEM lane quarter, alternating 32-column chunks). tcgen05.ld the accumulator
-//              (thread = row), fuse bias / timestep-embedding vector / residual / GEGLU, convert to 16 bit, store.
-//              Latency-bound, so: bias staged in smem per tile, residual prefetched one chunk ahead.
+//              (thread = row), fuse bias / timestep-embedding vector / residual / GEGLU, convert to 16 bit, write the
+//              32 x 32 chunk into a swizzled staging buffer and TMA-store it; the residual chunk is TMA-loaded into
+//              the same buffer one chunk ahead and updated in place. Bias staged in smem per tile.
 #include "gemm.cuh"
 #include <algorithm>
 #include <cstdio>
@@ -30,48 +30,14 @@ static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 static constexpr int TMEM_COLS = 512;
 static constexpr int SBIAS_BYTES = 2 * 256 * 4;  // per-tile bias slice in smem, double buffered
-
-template <bool BF16>
-struct Epi {
-  using T = T16<BF16>;
-
-  // 8 consecutive output columns of one row -> one 16-byte store
-  static SDXE_DEVINL void store8(void* dst, const float* v) {
-    uint4 u;
-    u.x = T::pack(v[0], v[1]);
-    u.y = T::pack(v[2], v[3]);
-    u.z = T::pack(v[4], v[5]);
-    u.w = T::pack(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst) = u;
-  }
-  static SDXE_DEVINL void add_bias8(float* v, const float* __restrict__ b, int n, int N) {
-    if (n + 8 <= N) {
-      float4 b0 = __ldg(reinterpret_cast<const float4*>(b + n));
-      float4 b1 = __ldg(reinterpret_cast<const float4*>(b + n + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (n + j < N) v[j] += __ldg(b + n + j);
-    }
-  }
-  static SDXE_DEVINL void add_res8(float* v, const void* res) {
-    uint4 u = *reinterpret_cast<const uint4*>(res);
-    float2 f;
-    f = T::unpack(u.x); v[0] += f.x; v[1] += f.y;
-    f = T::unpack(u.y); v[2] += f.x; v[3] += f.y;
-    f = T::unpack(u.z); v[4] += f.x; v[5] += f.y;
-    f = T::unpack(u.w); v[6] += f.x; v[7] += f.y;
-  }
-};
+static constexpr int CHUNK_BYTES = 32 * 32 * 2;   // one epilogue chunk: 32 rows x 32 columns, 16 bit
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int NUM_BARS_FIXED = 4 + 2 * NUM_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][2]
 
 // EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
 template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
-  using E = Epi<BF16>;
-  using TT = typename T16<BF16>::type;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -87,8 +53,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + 8 * (2 * S + 4));
-  float* sbias = reinterpret_cast<float*>(smem + S * stage_bytes + 8 * (2 * S + 4) + 16);  // [2][256]
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * S + 4 + 2 * w + b); };
+  const uint32_t misc_off = S * stage_bytes + 8 * (2 * S + NUM_BARS_FIXED);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + misc_off);
+  float* sbias = reinterpret_cast<float*>(smem + misc_off + 16);  // [2][256]
+  constexpr int NBUF = RES ? 2 : 1;  // staging chunks per epilogue warp (residual in flight needs the second one)
+  const uint32_t stage_buf_base = (smem_base + misc_off + 16 + SBIAS_BYTES + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +88,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), clustered ? 16 : 8);  // paired: both CTAs' epilogue warps free the leader's accumulator
     }
+    if (RES)
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
     fence_mbar_init();
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
@@ -242,60 +214,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Row-per-thread (the only way tcgen05.ld hands out data). Latency-bound, so every global read is taken off the
-    // critical path: the tile's bias goes to shared memory once per tile (zeros when there is none: no branch), the
-    // residual row piece of the next chunk is prefetched into registers while the current chunk is converted and
-    // stored, and full interior chunks take a guard-free, fully unrolled path.
+    // Row-per-thread (the only way tcgen05.ld hands out data): a thread owns 64 contiguous bytes of one output row per
+    // chunk, so direct global accesses would touch 32 different 128-byte lines per warp instruction (measured: the
+    // store path alone held every small-K GEMM at ~1.5 TB/s). The chunk is therefore staged in shared memory (TMA
+    // 64B / 32B swizzle = conflict-free 16-byte row pieces) and moved by TMA in both directions; out-of-range rows and
+    // columns are clipped (stores) or zero-filled (residual) by the tensor maps, so the loop carries no guards.
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warps w and w+4 share it)
-    const int ehalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
+    const int ew = warp - 2;             // 0..7
+    const int ehalf = ew >> 2;           // the two warps of a quarter take alternate 32-column chunks
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;     // 0..255 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t tile_ctr = 0;
+    uint32_t chunk_ctr = 0;              // chunks this warp has handled: staging buffer / barrier parity
     constexpr bool GEGLU = EPI == EPI_GEGLU;
-    const int Nst = GEGLU ? (a.N / 2) : ((a.N + 7) & ~7);
     const int out_cols = GEGLU ? (BN >> 1) : BN;  // output columns produced per tile
     const int half = BN >> 1;
-    const int C_heads = a.heads * a.head_dim;
-    const TT* resid = reinterpret_cast<const TT*>(a.residual);
-    TT* const outp = reinterpret_cast<TT*>(a.out);
     const float* const biasp = a.bias;
-    const int M = a.M, N = a.N, ldo = a.ldo, ldr = a.ldr;
+    const int M = a.M, N = a.N;
+    const uint32_t my_buf = stage_buf_base + (uint32_t)(ew * NBUF) * CHUNK_BYTES;
     for (int tile = work_first; tile < num_tiles; tile += work_step, ++tile_ctr) {
       const int n_blk = tile % num_n;
       const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
       const int m = m_blk * BLOCK_M + row;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;  // first row of this warp's band
       const bool row_ok = m < M;
       const int n_out0 = n_blk * out_cols;  // first output column of this tile
       float* sb = sbias + (tile_ctr & 1u) * 256;
       for (int j = et; j < BN; j += 256) sb[j] = (biasp != nullptr && n_blk * BN + j < N) ? __ldg(biasp + n_blk * BN + j) : 0.f;
-      uint4 res_cur[4], res_nxt[4];
-      const TT* res_row = RES ? resid + (size_t)m * ldr + n_out0 : nullptr;
-      auto prefetch = [&](int c0, uint4* dst) {
-        if (RES) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cc = c0 + g * 8;
-            if (row_ok && cc < out_cols && n_out0 + cc + 8 <= Nst) dst[g] = *reinterpret_cast<const uint4*>(res_row + cc);
-            else dst[g] = make_uint4(0, 0, 0, 0);
-          }
-        }
+      auto res_load = [&](int c0, uint32_t ctr) {  // elected lane: residual chunk -> staging buffer ctr & 1
+        const uint32_t b = ctr & 1u;
+        const int nc = min(32, out_cols - c0);
+        mbar_expect_tx(res_bar(ew, b), (uint32_t)nc * 64u);
+        tma_load_2d(my_buf + b * CHUNK_BYTES, nc == 32 ? &a.tmR : &a.tmR16, res_bar(ew, b), n_out0 + c0, row0);
       };
-      prefetch(ehalf * 32, res_cur);
+      if (RES && ehalf * 32 < out_cols) {  // (a tile narrower than 33 columns leaves the second warp of a quarter idle)
+        // first chunk's residual travels while the accumulator is still being produced
+        if (elect_one()) { bulk_wait_read_all(); res_load(ehalf * 32, chunk_ctr); }
+        __syncwarp();
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
       if (ROWVEC && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv + n_out0;
-      TT* const out_row = outp + (size_t)m * ldo + n_out0;
-      int hb = 0, htok = 0;
-      if (EPI == EPI_HEADS) { hb = m / a.tokens; htok = m - hb * a.tokens; }
-      const bool tile_full = row_ok && (n_out0 + out_cols <= Nst);
+      const bool cols_full = n_out0 + out_cols <= N;
 
-      for (int c0 = ehalf * 32; c0 < out_cols; c0 += 64) {
+      for (int c0 = ehalf * 32; c0 < out_cols; c0 += 64, ++chunk_ctr) {
         const int nc = min(32, out_cols - c0);
+        const uint32_t b = RES ? (chunk_ctr & 1u) : 0u;
+        const uint32_t buf = my_buf + b * CHUNK_BYTES;
         uint32_t r[32];
         uint32_t rg[GEGLU ? 32 : 1];
         if (nc == 32) tmem_ld32(t_row + c0, r);
@@ -304,21 +274,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           if (nc == 32) tmem_ld32(t_row + half + c0, rg);
           else tmem_ld16(t_row + half + c0, rg);
         }
-        if (c0 + 64 < out_cols) prefetch(c0 + 64, res_nxt);
-        tc_wait_ld();
-        // head-scatter bookkeeping advances incrementally (no divisions in the loop)
-        int h_which = 0, h_head = 0, h_off = 0;
-        if (EPI == EPI_HEADS) {
-          const int n = n_out0 + c0;
-          h_which = n / C_heads;
-          const int cc = n - h_which * C_heads;
-          h_head = cc / a.head_dim;
-          h_off = cc - h_head * a.head_dim;
+        if (RES) {
+          // the other buffer is free once the previous chunk's store has read it: fetch the next residual chunk into it
+          if (elect_one()) {
+            bulk_wait_read_all();
+            if (c0 + 64 < out_cols) res_load(c0 + 64, chunk_ctr + 1);
+          }
+          __syncwarp();
+          mbar_wait(res_bar(ew, b), (chunk_ctr >> 1) & 1u);
         }
-        const bool fast = tile_full && nc == 32;
+        tc_wait_ld();
+        // this thread's row piece inside the chunk: 16-byte unit g at (lane * rowbytes + 16 g) ^ swizzle
+        const uint32_t lin0 = (uint32_t)lane * (uint32_t)(nc * 2);
+        const uint32_t swz_mask = nc == 32 ? 3u : 1u;  // 64B / 32B swizzle: unit index ^= address bits [7, 8] / [7]
+        uint4 packed[4];
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
-          if (fast || g < nc) {
+          if (g < nc) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
@@ -339,7 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             }
             if (ROWVEC) {
               if (rv) {
-                if (fast || n_out0 + c0 + g + 8 <= N) {
+                if (cols_full || n_out0 + c0 + g + 8 <= N) {
                   const float4 e0 = __ldg(reinterpret_cast<const float4*>(rv + c0 + g)), e1 = __ldg(reinterpret_cast<const float4*>(rv + c0 + g + 4));
                   v[0] += e0.x; v[1] += e0.y; v[2] += e0.z; v[3] += e0.w;
                   v[4] += e1.x; v[5] += e1.y; v[6] += e1.z; v[7] += e1.w;
@@ -350,32 +322,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                 }
               }
             }
-            if (fast || (row_ok && n_out0 + c0 + g + 8 <= Nst)) {
-              if (EPI == EPI_HEADS) {  // column -> (which tensor, head, offset); row -> (batch, token)
-                TT* dst = reinterpret_cast<TT*>(a.outs[h_which]) + ((size_t)(hb * a.heads + h_head) * a.tokens + htok) * a.head_pad + h_off;
-                E::store8(dst, v);
-              } else {
-                if (RES) {
-                  float2 f;
-                  const uint4 u = res_cur[g >> 3];
-                  f = T16<BF16>::unpack(u.x); v[0] += f.x; v[1] += f.y;
-                  f = T16<BF16>::unpack(u.y); v[2] += f.x; v[3] += f.y;
-                  f = T16<BF16>::unpack(u.z); v[4] += f.x; v[5] += f.y;
-                  f = T16<BF16>::unpack(u.w); v[6] += f.x; v[7] += f.y;
-                }
-                E::store8(out_row + c0 + g, v);
-              }
+            if (RES) {
+              const uint32_t lin = lin0 + (uint32_t)(g * 2);
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                           : "r"(buf + (lin ^ (((lin >> 7) & swz_mask) << 4))));
+              float2 f;
+              f = T16<BF16>::unpack(u.x); v[0] += f.x; v[1] += f.y;
+              f = T16<BF16>::unpack(u.y); v[2] += f.x; v[3] += f.y;
+              f = T16<BF16>::unpack(u.z); v[4] += f.x; v[5] += f.y;
+              f = T16<BF16>::unpack(u.w); v[6] += f.x; v[7] += f.y;
             }
-            if (EPI == EPI_HEADS) {
-              h_off += 8;
-              if (h_off >= a.head_dim) { h_off = 0; if (++h_head == a.heads) { h_head = 0; ++h_which; } }
-            }
+            packed[g >> 3].x = T16<BF16>::pack(v[0], v[1]);
+            packed[g >> 3].y = T16<BF16>::pack(v[2], v[3]);
+            packed[g >> 3].z = T16<BF16>::pack(v[4], v[5]);
+            packed[g >> 3].w = T16<BF16>::pack(v[6], v[7]);
           }
         }
-        if (RES) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
+        if (!RES) {
+          // single staging buffer: the previous chunk's store must have read it before it is overwritten
+          if (elect_one()) bulk_wait_read_all();
+          __syncwarp();
         }
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+          if (g < nc) {
+            const uint32_t lin = lin0 + (uint32_t)(g * 2);
+            const uint4 u = packed[g >> 3];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(buf + (lin ^ (((lin >> 7) & swz_mask) << 4))), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(nc == 32 ? &a.tmO : &a.tmO16, buf, n_out0 + c0, row0);
+          bulk_commit_group();
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -386,6 +372,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (elect_one()) bulk_wait_all();  // all of this warp's stores have reached global memory
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -416,10 +404,32 @@ bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn) {
   return true;
 }
 
-int gemm_pick_stages(int BN) {
+static size_t gemm_smem_fixed(int num_stages, bool residual) {  // everything but the operand stages
+  return 1024 /*base alignment*/ + 8 * (2 * num_stages + NUM_BARS_FIXED) + 16 + SBIAS_BYTES + 1024 /*staging alignment*/ +
+         (size_t)NUM_EPI_WARPS * (residual ? 2 : 1) * CHUNK_BYTES;
+}
+int gemm_pick_stages(int BN, bool residual) {
   const int stage_bytes = A_STAGE_BYTES + BN * 128;
-  int s = (227 * 1024 - 2048 - SBIAS_BYTES) / stage_bytes;
+  int s = (int)((227 * 1024 - gemm_smem_fixed(8, residual)) / stage_bytes);
   return std::max(2, std::min(s, 8));
+}
+int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld) {
+  a.cluster = gemm_pick_cluster(a.M, a.BN);
+  const int bn_cta = a.cluster == 2 ? a.BN / 2 : a.BN;
+  a.num_stages = gemm_pick_stages(bn_cta, a.residual != nullptr);
+  if (make_tmap_2d(&a.tmB, W, w_rows, a.K, w_ld, bn_cta)) return -1;
+  const int64_t out_cols = a.epi == EPI_GEGLU ? a.N / 2 : (a.N + 7) / 8 * 8;
+  if (a.ldo % 8 || (a.residual && a.ldr % 8)) { set_last_error(__FILE__, __LINE__, "gemm: ldo / ldr must be multiples of 8"); return -1; }
+  if (make_tmap_2d_box(&a.tmO, a.out, a.M, std::min<int64_t>(out_cols, a.ldo), a.ldo, 32, 32)) return -1;
+  if (make_tmap_2d_box(&a.tmO16, a.out, a.M, std::min<int64_t>(out_cols, a.ldo), a.ldo, 16, 32)) return -1;
+  if (a.residual) {
+    if (make_tmap_2d_box(&a.tmR, a.residual, a.M, std::min<int64_t>(out_cols, a.ldr), a.ldr, 32, 32)) return -1;
+    if (make_tmap_2d_box(&a.tmR16, a.residual, a.M, std::min<int64_t>(out_cols, a.ldr), a.ldr, 16, 32)) return -1;
+  } else {
+    a.tmR = a.tmO;
+    a.tmR16 = a.tmO16;
+  }
+  return 0;
 }
 
 int gemm_pick_bn(int M, int N, int K, int epi) {
@@ -442,7 +452,7 @@ int gemm_pick_bn(int M, int N, int K, int epi) {
 }
 
 typedef void (*GemmKernel)(const GemmArgs);
-// variant index = cluster * 12 + bf16 * 6 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu, 5: heads}
+// variant index = cluster * 10 + bf16 * 5 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu}
 template <bool BF16, bool CL>
 static GemmKernel gemm_variant_e(int e) {
   switch (e) {
@@ -450,12 +460,11 @@ static GemmKernel gemm_variant_e(int e) {
     case 1: return gemm_kernel<BF16, EPI_PLAIN, true, false, CL>;
     case 2: return gemm_kernel<BF16, EPI_PLAIN, false, true, CL>;
     case 3: return gemm_kernel<BF16, EPI_PLAIN, true, true, CL>;
-    case 4: return gemm_kernel<BF16, EPI_GEGLU, false, false, CL>;
-    default: return gemm_kernel<BF16, EPI_HEADS, false, false, CL>;
+    default: return gemm_kernel<BF16, EPI_GEGLU, false, false, CL>;
   }
 }
 static GemmKernel gemm_variant(int i) {
-  const int cl = i / 12, bf = (i % 12) / 6, e = i % 6;
+  const int cl = i / 10, bf = (i % 10) / 5, e = i % 5;
   if (cl) return bf ? gemm_variant_e<true, true>(e) : gemm_variant_e<false, true>(e);
   return bf ? gemm_variant_e<true, false>(e) : gemm_variant_e<false, false>(e);
 }
@@ -463,7 +472,7 @@ static GemmKernel gemm_variant(int i) {
 int gemm_init() {
   static bool done = false;
   if (!done) {
-    for (int i = 0; i < 24; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 20; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done = true;
   }
   return 0;
@@ -474,7 +483,8 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
   const int stage_bytes = A_STAGE_BYTES + (a.cluster == 2 ? a.BN / 2 : a.BN) * 128;
-  const size_t smem = (size_t)a.num_stages * stage_bytes + 8 * (2 * a.num_stages + 4) + 16 + SBIAS_BYTES + 1024;
+  const size_t smem = (size_t)a.num_stages * stage_bytes + gemm_smem_fixed(a.num_stages, a.residual != nullptr);
+  if (smem > 227 * 1024) { set_last_error(__FILE__, __LINE__, "gemm: shared memory budget"); return -1; }
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
   const int tiles = num_m * num_n;
   if (tiles <= 0) return 0;
@@ -483,9 +493,9 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
     if ((num_m & 1) || (a.BN % 16)) { set_last_error(__FILE__, __LINE__, "gemm: cluster needs an even m-tile count"); return -1; }
     grid = std::min(tiles, num_sms() & ~1);
   }
-  int vi = a.epi == EPI_GEGLU ? 4 : (a.epi == EPI_HEADS ? 5 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0)));
+  const int vi = a.epi == EPI_GEGLU ? 4 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0));
   if ((a.epi != EPI_PLAIN) && (a.residual || a.rowvec)) { set_last_error(__FILE__, __LINE__, "gemm: residual / rowvec need EPI_PLAIN"); return -1; }
-  GemmKernel kern = gemm_variant(vi + (bf16 ? 6 : 0) + (a.cluster == 2 ? 12 : 0));
+  GemmKernel kern = gemm_variant(vi + (bf16 ? 5 : 0) + (a.cluster == 2 ? 10 : 0));
   if (gemm_init() != 0) return -1;
   if (a.cluster == 2) {
     cudaLaunchConfig_t cfg;

@@ -7,13 +7,17 @@ namespace sdxe {
 enum : int {
   EPI_PLAIN = 0,  // out[m, n] = acc (+bias +rowvec +residual)
   EPI_GEGLU = 1,  // out[m, j] = (acc[j] + b[j]) * gelu(acc[BN/2 + j] + b[BN/2 + j]); weights pre-interleaved per tile
-  EPI_HEADS = 2,  // scatter columns into per-head padded [B, heads, tokens, head_pad] tensors (q / k / v)
 };
 
 struct alignas(64) GemmArgs {
   CUtensorMap tmA;   // 2D: [M, K1] 16-bit, box 64 x 128.  conv: NHWC [N,H,W,C], box 64 x bw x bh x bn
   CUtensorMap tmA2;  // optional second K segment (skip-concat read as two K-segments), 2D only
   CUtensorMap tmB;   // weights [N, K] K-contiguous, box 64 x BN
+  // epilogue: every output chunk (32 rows x 32 columns of one epilogue warp) leaves through a TMA store from a swizzled
+  // staging buffer, the residual chunk arrives the same way (whole 64-byte row pieces -> full-line L2 transactions
+  // instead of 32 scattered 16-byte accesses per warp instruction). The *16 maps serve a tile's 16-column tail chunk.
+  CUtensorMap tmO, tmO16;  // out [M, ldo]: box 32 x 32 (64B swizzle) / 16 x 32 (32B swizzle); rows >= M, cols >= N clipped
+  CUtensorMap tmR, tmR16;  // residual [M, ldr], same boxes (only when residual != null)
   int M, N, K;       // problem (conv: K = 9 * Cin, M = N_img * H * W)
   int K1;            // K elements sourced from tmA (== K when there is no second segment)
   int BN;            // tile width (multiple of 16, <= 256)
@@ -32,9 +36,6 @@ struct alignas(64) GemmArgs {
   const void* residual;  // [M, ldr] 16-bit or null
   void* out;             // [M, ldo] 16-bit
   int ldo;
-  // EPI_HEADS
-  int heads, head_dim, head_pad, tokens;
-  void* outs[3];
 };
 
 // Launch on `stream`. bf16 selects the 16-bit format of A/B/out/residual. Returns 0 / -1.
@@ -42,8 +43,11 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream);
 int gemm_init();  // one-time kernel attribute setup (call before any stream capture)
 // Tile-width heuristic: pick BN for an [M, N] output (geglu needs BN % 32 == 0 and N % BN == 0).
 int gemm_pick_bn(int M, int N, int K, int epi);
-int gemm_pick_stages(int BN);
-int gemm_pick_cluster(int M, int BN);  // 2 when CTA pairs can share the B tile (TMA multicast), else 1
+int gemm_pick_stages(int BN, bool residual);
+int gemm_pick_cluster(int M, int BN);  // 2 when CTA pairs (cta_group::2) are enabled and the geometry allows, else 1
+// After M/N/K/K1/BN/epi/tmA/out/ldo/residual/ldr are set: picks cluster + stage count, builds tmB over the packed
+// weights W [w_rows, K] (row pitch w_ld) and the epilogue's store / residual maps.
+int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld);
 // 128-pixel tile of the implicit-GEMM conv as a TMA box (bw x bh x bn); false if (H, W) needs the im2col path.
 bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn);
 

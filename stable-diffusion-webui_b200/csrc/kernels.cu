@@ -403,22 +403,6 @@ int cast_rows_launch(const void* src, int src_dtype, void* dst, int64_t rows, in
   return 0;
 }
 
-__global__ void pad_heads_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t rows, int D, int Dpad) {
-  const int64_t total = rows * Dpad;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / Dpad;
-    const int c = (int)(idx - r * Dpad);
-    dst[idx] = c < D ? src[r * D + c] : (uint16_t)0;
-  }
-}
-
-int pad_heads_launch(const void* src, void* dst, int64_t rows, int D, int Dpad, cudaStream_t s) {
-  const int64_t total = rows * Dpad;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
-  pad_heads_kernel<<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, rows, D, Dpad);
-  SDXE_LAUNCH_CHECK();
-  return 0;
-}
 
 // =============================================================================================================
 // embeddings

@@ -27,8 +27,6 @@ int upsample2x_launch(const void* x, void* out, int n, int H, int W, int C, cuda
 int nhwc_to_nchw_launch(const void* in, int ld, void* out, int io_dtype, int n, int C, int hw, bool bf16, cudaStream_t s);
 // generic cast of a contiguous [rows, cols] (src dtype) into 16-bit [rows, ldo] (pad columns untouched)
 int cast_rows_launch(const void* src, int src_dtype, void* dst, int64_t rows, int cols, int ldo, bool bf16, cudaStream_t s);
-// [BH, N, D] -> [BH, N, Dpad] zero padded (stand-alone attention entry)
-int pad_heads_launch(const void* src, void* dst, int64_t rows, int D, int Dpad, cudaStream_t s);
 
 // ---- embeddings --------------------------------------------------------------------------------------------
 // modules/sd_hijack_unet.py:58-78: emb[m, :] = [cos(t*f) , sin(t*f)], rounded through the 16-bit type; fp32 out.
