@@ -331,9 +331,10 @@ int attention_init() {
 int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   AttnArgs a = a_in;
   {
-    static int use2 = -1;
-    if (use2 < 0) { const char* e = getenv("SDXE_ATTN2"); use2 = e ? atoi(e) : 1; }
-    if (use2 && attention2_eligible(a)) return attention2_launch(a, bf16, stream);
+    // SDXE_ATTN: 2 = attention2 (two Q tiles per CTA) where eligible [default], 1 = this file's kernel only
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SDXE_ATTN"); mode = e ? atoi(e) : 2; }
+    if (mode == 2 && attention2_eligible(a)) return attention2_launch(a, bf16, stream);
   }
   if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {
     set_last_error(__FILE__, __LINE__, "attention: unsupported head size");
