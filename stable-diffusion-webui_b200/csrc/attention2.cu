@@ -187,12 +187,28 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
 #pragma unroll
         for (int vs = 0; vs < 2; ++vs)
           if (vs < VS) vd[vs] = umma_desc_sw128(pop(v_slot[vs]), SLAB2, 1024);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(p_ready(t), (uint32_t)(i & 1));
-          tc_fence_after();
-          if (more) issue_s(t);
-          issue_pv(t, i);
+        // the two tiles are served in ARRIVAL order (a tile that finishes its softmax first must not wait for the
+        // other one's p_ready: that is what lets the tiles drift half a period apart and alternate on the MUFU pipe)
+        {
+          bool served0 = false, served1 = false;
+          for (uint32_t spin = 0; !(served0 && served1); ++spin) {
+            if (!served0 && __any_sync(0xffffffffu, mbar_test(p_ready(0), (uint32_t)(i & 1)))) {
+              tc_fence_after();
+              if (more) issue_s(0);
+              issue_pv(0, i);
+              served0 = true;
+            }
+            if (!served1 && __any_sync(0xffffffffu, mbar_test(p_ready(1), (uint32_t)(i & 1)))) {
+              tc_fence_after();
+              if (more) issue_s(1);
+              issue_pv(1, i);
+              served1 = true;
+            }
+            if (spin > (1u << 28)) {
+              printf("sdxe: attention2 MMA warp watchdog block(%d,%d) i %d\n", blockIdx.x, blockIdx.y, i);
+              __trap();
+            }
+          }
         }
         if (more) release(k_slot, QS);
         release(v_slot, VS);

@@ -76,6 +76,19 @@ SDXE_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Non-blocking probe of a phase (for a consumer that serves several producers in arrival order).
+SDXE_DEVINL bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // generic-proxy smem writes -> visible to async proxy (TMA / tcgen05.mma operand reads)
 SDXE_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
