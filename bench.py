@@ -358,6 +358,12 @@ def main():
         mm_n = prof_u["gemm"]["launches"] + prof_u["conv3x3"]["launches"]
         achieved = mm_fl / (mm_ms / 1000.0) / 1e12 if mm_ms > 0 else 0.0
         total_u = sum(v["ms"] for v in prof_u.values())
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1c_gemm_traffic.json")
+        if args.config == "sd15" and os.path.exists(tpath):  # ncu capture of the same kernel on the same UNet call (SD1.5, 2B = 16)
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["traffic_per_launch_bytes"], tj["source"]
         roofline = {"bound": "tensor", "kernel": "sdxe::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved,
                     "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                     "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)", "traffic": None,
