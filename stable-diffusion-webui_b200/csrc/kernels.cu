@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels: GroupNorm / LayerNorm, layout gathers, embeddings, weight repack, sampler-step fusions.
 // All activation tensors are 16-bit NHWC ([n, h*w, c]); vectors of 8 channels (16 B) per thread access.
 #include "kernels.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <atomic>
 
@@ -152,11 +153,90 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint
   }
 }
 
+// One-pass GroupNorm for the UNet's shapes: one CTA per (sample, group) keeps the group's [hw, C/groups] strip in shared
+// memory — one global read, fp32 two-pass statistics (mean, then centred second moment) from smem, one global write.
+// Replaces stats + finalize + apply (2 reads, 1 write, 3 launches) for the small tensors (strip hw * cpg * 2 B <= 48 KB:
+// the 8x8 / 16x16 and narrow 32x32 levels, where the three launches are latency-bound); larger tensors keep the
+// three-kernel streaming path (measured: 64x64x320 39 us vs 62 us one-pass).
+// Thread -> (pixel lane, channel pair): the channel pair is fixed per thread, so gamma / beta / source pointer live in
+// registers and the loops carry no divisions. Fixed reduction order: bit-identical on replay.
+template <bool BF16, bool SILU>
+__global__ void __launch_bounds__(512) gn_onepass_kernel(const uint32_t* __restrict__ x1, int c1, const uint32_t* __restrict__ x2, int c2,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  uint32_t* __restrict__ out, int hw, int groups, float eps) {
+  extern __shared__ uint32_t gn_tile[];  // [hw][W] packed channel pairs
+  __shared__ float red[16];
+  __shared__ float bcast;
+  const int C = c1 + c2, cpg = C / groups, W = cpg >> 1;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int R = blockDim.x / W;                 // pixels per sweep
+  const int pl = threadIdx.x / W, w = threadIdx.x - pl * W;
+  const bool active = pl < R;
+  const int c = g * cpg + 2 * w;                // first channel of this thread's pair
+  const uint32_t* src = (c < c1) ? x1 : x2;
+  const int cs = (c < c1) ? c1 : c2, co = (c < c1) ? c : c - c1;
+  const size_t pix0 = (size_t)n * hw;
+  auto block_sum = [&](float v) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // red / bcast reusable
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) bcast = t;
+    }
+    __syncthreads();
+    return bcast;
+  };
+  float s = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int p = pl; p < hw; p += R) {
+      const uint32_t u = __ldg(src + (((pix0 + p) * cs + co) >> 1));
+      gn_tile[p * W + w] = u;
+      const float2 f = T16<BF16>::unpack(u);
+      s += f.x + f.y;
+    }
+  }
+  const float inv_cnt = 1.f / ((float)hw * (float)cpg);
+  const float mean = block_sum(s) * inv_cnt;
+  float q = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int p = pl; p < hw; p += R) {  // own elements only: no cross-thread smem dependency
+      const float2 f = T16<BF16>::unpack(gn_tile[p * W + w]);
+      const float a = f.x - mean, b = f.y - mean;
+      q += a * a + b * b;
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q) * inv_cnt + eps);
+  if (active) {
+    const float sc0 = rstd * __ldg(gamma + c), sc1 = rstd * __ldg(gamma + c + 1);
+    const float sh0 = __ldg(beta + c) - mean * sc0, sh1 = __ldg(beta + c + 1) - mean * sc1;
+    uint32_t* dst = out + ((pix0 * C + c) >> 1);
+    const int Ch = C >> 1;
+#pragma unroll 4
+    for (int p = pl; p < hw; p += R) {
+      const float2 f = T16<BF16>::unpack(gn_tile[p * W + w]);
+      float y0 = fmaf(f.x, sc0, sh0), y1 = fmaf(f.y, sc1, sh1);
+      if (SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      dst[(size_t)p * Ch] = T16<BF16>::pack(y0, y1);
+    }
+  }
+}
+
 int kernels_init() {
   static bool done = false;
   if (!done) {
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     done = true;
   }
   return 0;
@@ -169,6 +249,27 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
   if (x2 == nullptr) c2 = 0;
   const int C = c1 + c2;
   if (C % 8 || c1 % 8 || C % groups) { set_last_error(__FILE__, __LINE__, "group_norm: channel alignment"); return -1; }
+  if (kernels_init() != 0) return -1;
+  {
+    static int onepass = -1;
+    if (onepass < 0) { const char* e = getenv("SDXE_GN_ONEPASS"); onepass = e ? atoi(e) : 1; }
+    const int cpg = C / groups;
+    const size_t strip = (size_t)hw * cpg * 2;
+    // measured crossover: one CTA per strip wins up to ~48 KB (enough CTAs per SM to hide its serial passes); the
+    // wide 64x64 / 32x32 tensors are faster through the three streaming kernels
+    if (onepass && cpg % 2 == 0 && cpg / 2 <= 256 && strip <= 48 * 1024) {
+      const int threads = strip >= 32 * 1024 ? 512 : 256;
+      dim3 grid(groups, n);
+#define GN_ONE(B, S)                                                                                                      \
+  gn_onepass_kernel<B, S><<<grid, threads, strip, s>>>((const uint32_t*)x1, c1, (const uint32_t*)x2, c2, gamma, beta, \
+                                                       (uint32_t*)out, hw, groups, eps)
+      if (bf16) { if (silu) GN_ONE(true, true); else GN_ONE(true, false); }
+      else { if (silu) GN_ONE(false, true); else GN_ONE(false, false); }
+#undef GN_ONE
+      SDXE_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const int V = C / 8;
   if (V > 1024) { set_last_error(__FILE__, __LINE__, "group_norm: too many channels"); return -1; }
   int rpi = std::max(1, 256 / V);
@@ -257,9 +358,69 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const uint4* __restrict
   }
 }
 
+// C = 40 * G channels (the UNet's 320 / 640 / 1280): G = 8 / 16 / 32 lanes per row, five 8-channel vectors per lane, so
+// every lane of the warp is busy (the generic kernel leaves 3/8 of its lanes idle at C = 320) and a warp covers 32 / G rows.
+template <bool BF16, int G>
+__global__ void __launch_bounds__(256) layer_norm5_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, uint4* __restrict__ out, int rows, float eps) {
+  constexpr int RPW = 32 / G, V = 5 * G, C = 8 * V;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row = warp * RPW + lane / G, gl = lane % G;
+  const bool ok = row < rows;
+  const uint4* xr = x + (size_t)row * V;
+  float f[5][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    if (ok) unpack8<BF16>(__ldg(xr + gl + G * i), f[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += f[i][j];
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / (float)C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.f / (float)C) + eps);
+  if (!ok) return;
+  uint4* orow = out + (size_t)row * V;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = gl + G * i;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = (f[i][j] - mean) * rstd * gm[j] + bt[j];
+    orow[v] = pack8<BF16>(y);
+  }
+}
+
 int layer_norm_launch(const void* x, const float* gamma, const float* beta, void* out, int rows, int c, float eps,
                       bool bf16, cudaStream_t s) {
   if (c % 8 || c > 2048) { set_last_error(__FILE__, __LINE__, "layer_norm: C % 8 != 0 or C > 2048"); return -1; }
+  if (c == 320 || c == 640 || c == 1280) {
+    const int G = c / 40, rpb = 8 * (32 / G);  // rows per 256-thread block
+    const int nb = (rows + rpb - 1) / rpb;
+#define LN5(B, GG) layer_norm5_kernel<B, GG><<<nb, 256, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, eps)
+    if (bf16) { if (G == 8) LN5(true, 8); else if (G == 16) LN5(true, 16); else LN5(true, 32); }
+    else { if (G == 8) LN5(false, 8); else if (G == 16) LN5(false, 16); else LN5(false, 32); }
+#undef LN5
+    SDXE_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per block
   const int nv = (c / 8 + 31) / 32;   // vectors per lane
 #define LN_LAUNCH(B, MV) layer_norm_kernel<B, MV><<<blocks, 256, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps)
