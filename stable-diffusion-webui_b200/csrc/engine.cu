@@ -68,7 +68,8 @@ struct ResW {
 };
 struct TBlockW {
   NormW ln1, ln2, ln3;
-  LinW qkv1, out1, q2, kv2, out2, ff1, ff2;
+  LinW qkv1, out1, q2, out2, ff1, ff2;
+  int kv_off = -1;  // column offset of this block's cross-attention [k | v] in the batched context projection
 };
 struct STW {
   NormW gn;
@@ -127,6 +128,11 @@ struct sdxe_engine {
   // UNet
   LinW te0, te2, le0, le2, emb_all;
   int emb_total = 0;
+  // every transformer block's attn2.to_k / to_v stacked along N: the context is projected ONCE per UNet call
+  LinW kv_all;
+  int kv_total = 0;
+  std::vector<std::string> kv_keys;
+  std::vector<int> kv_rows;
   std::vector<BlockW> in_blocks, out_blocks;
   ResW mid_r1, mid_r2;
   STW mid_st;
@@ -401,7 +407,8 @@ struct Builder {
   }
 
   // SpatialTransformer (modules/sd_hijack_unet.py:83-102) with BasicTransformerBlocks
-  int spatial_transformer(const STW& st, Act& x, const void* ctx16, int ctx_len, int ctx_dim, Act& out) {
+  // kv_all: [B * ctx_len, ld_kv] = every block's cross-attention k | v projection of the context (one GEMM per call)
+  int spatial_transformer(const STW& st, Act& x, const void* kv_all, int ld_kv, int ctx_len, Act& out) {
     const int C = st.C, H = st.heads, dh = st.dh;
     const int64_t M = x.rows();
     const int tokens = x.h * x.w, B = x.n;
@@ -431,11 +438,9 @@ struct Builder {
       ECHK(layer_norm(h.p, M, tb.ln2, ln.p));
       Act q2 = new_act(x.n, x.h, x.w, C);
       ECHK(gemm(ln.p, C, M, tb.q2, q2.p, GemmOpt()));
-      Act kv2 = new_act(B, 1, ctx_len, 2 * C);  // columns: [k | v]
-      ECHK(gemm(ctx16, ctx_dim, (int64_t)B * ctx_len, tb.kv2, kv2.p, GemmOpt()));
-      ECHK(attention(q2.p, kv2.p, (const uint16_t*)kv2.p + C, B, H, tokens, ctx_len, dh, C, 2 * C, scale, att.p, C, dh));
+      const uint16_t* kv = (const uint16_t*)kv_all + tb.kv_off;  // columns: [k | v] of this block
+      ECHK(attention(q2.p, kv, kv + C, B, H, tokens, ctx_len, dh, C, ld_kv, scale, att.p, C, dh));
       free_act(q2);
-      free_act(kv2);
       Act h3 = new_act(x.n, x.h, x.w, C);
       GemmOpt oo2;
       oo2.residual = h.p; oo2.ldr = C;
@@ -611,7 +616,10 @@ int sdxe_engine::build_st(STW& s, const std::string& p, int C, int depth) {
     ECHK(pack_linear(t.qkv1, {b + ".attn1.to_q.weight", b + ".attn1.to_k.weight", b + ".attn1.to_v.weight"}, {}, C, C, PACK_PLAIN));
     ECHK(pack_linear(t.out1, {b + ".attn1.to_out.0.weight"}, {b + ".attn1.to_out.0.bias"}, C, C, PACK_PLAIN));
     ECHK(pack_linear(t.q2, {b + ".attn2.to_q.weight"}, {}, C, C, PACK_PLAIN));
-    ECHK(pack_linear(t.kv2, {b + ".attn2.to_k.weight", b + ".attn2.to_v.weight"}, {}, C, ctx, PACK_PLAIN));
+    t.kv_off = kv_total;  // packed after all blocks are known (build_unet)
+    kv_keys.push_back(b + ".attn2.to_k.weight"); kv_rows.push_back(C);
+    kv_keys.push_back(b + ".attn2.to_v.weight"); kv_rows.push_back(C);
+    kv_total += 2 * C;
     ECHK(pack_linear(t.out2, {b + ".attn2.to_out.0.weight"}, {b + ".attn2.to_out.0.bias"}, C, C, PACK_PLAIN));
     const int n1 = 8 * C;
     const int tile = n1 % 256 == 0 ? 256 : (n1 % 128 == 0 ? 128 : 64);
@@ -630,6 +638,7 @@ int sdxe_engine::build_unet() {
     ECHK(pack_linear(le2, {"label_emb.0.2.weight"}, {"label_emb.0.2.bias"}, ted, ted, PACK_PLAIN));
   }
   in_blocks.clear(); out_blocks.clear();
+  kv_keys.clear(); kv_rows.clear(); kv_total = 0;
   std::vector<std::string> emb_w, emb_b;  // batched emb_layers (every ResBlock's Linear(SiLU(emb)) in one skinny GEMM)
   std::vector<int> emb_n;
   int emb_cursor = 0;
@@ -728,6 +737,20 @@ int sdxe_engine::build_unet() {
       ECHK(pack_vector_launch(b->dev, b->dtype, emb_all.b + off, emb_n[i], 0, true, bf16, 0));
     }
     off += emb_n[i];
+  }
+  // batched cross-attention K/V projection weights [kv_total, context_dim]
+  {
+    const int ctx = cfg.context_dim;
+    kv_all.N = kv_total; kv_all.K = ctx; kv_all.ld = ctx; kv_all.b = nullptr;
+    kv_all.Nrows = (int)align_up((size_t)kv_total, 16);
+    kv_all.w = alloc16((size_t)kv_all.Nrows * ctx);
+    int row = 0;
+    for (size_t i = 0; i < kv_keys.size(); ++i) {
+      const RawWeight* w = find(kv_keys[i], (int64_t)kv_rows[i] * ctx);
+      if (!sizing && w)
+        ECHK(pack_weight_launch(w->dev, w->dtype, (char*)kv_all.w + (size_t)row * ctx * 2, PACK_PLAIN, kv_rows[i], ctx, ctx, 0, bf16, 0));
+      row += kv_rows[i];
+    }
   }
   return 0;
 }
@@ -915,6 +938,9 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
   }
   const float* emb_ptr = (const float*)emb_all.p;
   const int ld_emb = e->emb_total;
+  // ---- cross-attention keys / values of ALL transformer blocks: one GEMM over the context (plan-owned buffer)
+  Buf kvbuf = e->alloc((size_t)n * ctx_len * std::max(8, e->kv_total) * 2);
+  if (e->kv_total > 0) ECHK(B.gemm(ctx16.p, cfg.context_dim, (int64_t)n * ctx_len, e->kv_all, kvbuf.p, Builder::GemmOpt()));
 
   // ---- input blocks
   std::vector<Act> hs;
@@ -932,7 +958,7 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
       // `cur` stays alive: it is on the skip stack
       if (b.has_st) {
         Act t;
-        ECHK(B.spatial_transformer(b.st, r, ctx16.p, ctx_len, cfg.context_dim, t));
+        ECHK(B.spatial_transformer(b.st, r, kvbuf.p, e->kv_total, ctx_len, t));
         B.free_act(r);
         r = t;
       }
@@ -950,7 +976,7 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
   {
     Act r1, t, r2;
     ECHK(B.res_block(e->mid_r1, cur, nullptr, emb_ptr, ld_emb, r1));
-    ECHK(B.spatial_transformer(e->mid_st, r1, ctx16.p, ctx_len, cfg.context_dim, t));
+    ECHK(B.spatial_transformer(e->mid_st, r1, kvbuf.p, e->kv_total, ctx_len, t));
     B.free_act(r1);
     ECHK(B.res_block(e->mid_r2, t, nullptr, emb_ptr, ld_emb, r2));
     B.free_act(t);
@@ -969,7 +995,7 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
     B.free_act(skip);
     if (b.has_st) {
       Act t;
-      ECHK(B.spatial_transformer(b.st, r, ctx16.p, ctx_len, cfg.context_dim, t));
+      ECHK(B.spatial_transformer(b.st, r, kvbuf.p, e->kv_total, ctx_len, t));
       B.free_act(r);
       r = t;
     }
@@ -1000,7 +1026,7 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
     const int oc = cfg.out_channels, hw = h * w;
     p->post.push_back([=](cudaStream_t s) { return nhwc_to_nchw_launch(ob, ldo, p->out, p->io_dtype, n, oc, hw, bf16, s); });
   }
-  // plan-owned buffers (col0, ctx16, temb, y32, e1, emb, l1, emb_all, outb) stay reserved for this plan
+  // plan-owned buffers (col0, ctx16, temb, y32, e1, emb, l1, emb_all, kvbuf, outb) stay reserved for this plan
   return 0;
 }
 
