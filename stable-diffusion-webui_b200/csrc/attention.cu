@@ -34,6 +34,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs a) {
   using T = T16<BF16>;
   using TT = typename T::type;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // q / k / v of the producing GEMM are complete; the output buffer is free
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
@@ -349,8 +351,7 @@ int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
   if (attention_init() != 0) return -1;
   dim3 grid((a.Nq + 127) / 128, a.B * a.H);
-  kern<<<grid, ATT_THREADS, smem, stream>>>(a);
-  SDXE_CUDA_CHECK(cudaGetLastError());
+  SDXE_CUDA_CHECK(launch_k(kern, grid, dim3(ATT_THREADS), smem, stream, a));
   return 0;
 }
 

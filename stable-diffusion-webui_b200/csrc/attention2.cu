@@ -25,6 +25,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __grid_constant__ AttnArgs a) {
   using T = T16<BF16>;
   using TT = typename T::type;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // q / k / v of the producing GEMM are complete; the output buffer is free
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
@@ -387,8 +389,7 @@ int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   if (attention2_init() != 0) return -1;
   auto kern = bf16 ? attention2_kernel<true> : attention2_kernel<false>;
   dim3 grid((a.Nq + 255) / 256, a.B * a.H);
-  kern<<<grid, ATT2_THREADS, smem, stream>>>(a);
-  SDXE_CUDA_CHECK(cudaGetLastError());
+  SDXE_CUDA_CHECK(launch_k(kern, grid, dim3(ATT2_THREADS), smem, stream, a));
   return 0;
 }
 

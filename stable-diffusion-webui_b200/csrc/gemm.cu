@@ -38,6 +38,7 @@ static constexpr int NUM_BARS_FIXED = 4 + 2 * NUM_EPI_WARPS;  // tfull[2], tempt
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
 template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   if (clustered) cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // the producing kernel's activations (A, residual) are complete; our output buffer is no longer read
 
   // Producer and MMA warps run their loops CONVERGED (all 32 lanes wait on the barriers) and only the asynchronous
   // issue itself is predicated on one elected lane. Issuing from inside a divergent `if (lane == 0)` region makes the
@@ -504,16 +506,18 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SDXE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
   } else {
-    kern<<<grid, GEMM_THREADS, smem, stream>>>(a);
+    SDXE_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, a));
   }
   SDXE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -55,6 +55,8 @@ SDXE_DEVINL float round16(float v) { return T16<BF16>::to_f(T16<BF16>::from_f(v)
 template <bool BF16>
 __global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint4* __restrict__ x2, int c2,
                                 float* __restrict__ partial, int hw, int groups, int pix_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // [rpi][C] sums, then [rpi][C] sums of squares
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int n = blockIdx.y;
@@ -92,6 +94,8 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, int c1, const uint
 
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int n_img, int chunks,
                                    int groups, float inv_cnt, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one warp per (image, group): lanes stride over the block partials, fixed-order tree reduce (deterministic)
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_img * groups) return;
@@ -123,6 +127,8 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, int c1, const uint
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, uint4* __restrict__ out, int hw, int groups,
                                 int pix_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int n = blockIdx.y;
   const int vec = threadIdx.x % V, prow = threadIdx.x / V, rpi = blockDim.x / V;
@@ -164,6 +170,8 @@ template <bool BF16, bool SILU>
 __global__ void __launch_bounds__(512) gn_onepass_kernel(const uint32_t* __restrict__ x1, int c1, const uint32_t* __restrict__ x2, int c2,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   uint32_t* __restrict__ out, int hw, int groups, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint32_t gn_tile[];  // [hw][W] packed channel pairs
   __shared__ float red[16];
   __shared__ float bcast;
@@ -261,8 +269,8 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
       const int threads = strip >= 32 * 1024 ? 512 : 256;
       dim3 grid(groups, n);
 #define GN_ONE(B, S)                                                                                                      \
-  gn_onepass_kernel<B, S><<<grid, threads, strip, s>>>((const uint32_t*)x1, c1, (const uint32_t*)x2, c2, gamma, beta, \
-                                                       (uint32_t*)out, hw, groups, eps)
+  SDXE_CUDA_CHECK(launch_k(gn_onepass_kernel<B, S>, grid, dim3(threads), strip, s, (const uint32_t*)x1, c1, (const uint32_t*)x2, c2, \
+                           gamma, beta, (uint32_t*)out, hw, groups, eps))
       if (bf16) { if (silu) GN_ONE(true, true); else GN_ONE(true, false); }
       else { if (silu) GN_ONE(false, true); else GN_ONE(false, false); }
 #undef GN_ONE
@@ -284,12 +292,12 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
   const size_t sm = sizeof(float) * 2 * rpi * C;
   if (kernels_init() != 0) return -1;
   if (bf16)
-    gn_stats_kernel<true><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb);
+    SDXE_CUDA_CHECK(launch_k(gn_stats_kernel<true>, grid, dim3(threads), sm, s, (const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb));
   else
-    gn_stats_kernel<false><<<grid, threads, sm, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb);
+    SDXE_CUDA_CHECK(launch_k(gn_stats_kernel<false>, grid, dim3(threads), sm, s, (const uint4*)x1, c1, (const uint4*)x2, c2, partial, hw, groups, ppb));
   SDXE_LAUNCH_CHECK();
   const float inv_cnt = 1.f / ((float)hw * (float)(C / groups));
-  gn_finalize_kernel<<<(n * groups + 3) / 4, 128, 0, s>>>(partial, stats, n, chunks, groups, inv_cnt, eps);
+  SDXE_CUDA_CHECK(launch_k(gn_finalize_kernel, dim3((n * groups + 3) / 4), dim3(128), 0, s, (const float*)partial, stats, n, chunks, groups, inv_cnt, eps));
   SDXE_LAUNCH_CHECK();
   // apply: finer pixel chunks than the statistics pass (pure streaming, wants every SM busy several times over)
   int achunks = std::max(1, std::min((num_sms() * 8 + n - 1) / n, (hw + rpi * 2 - 1) / (rpi * 2)));
@@ -297,8 +305,8 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
   achunks = (hw + appb - 1) / appb;
   dim3 agrid(achunks, n);
 #define GN_APPLY(B, S)                                                                                              \
-  gn_apply_kernel<B, S><<<agrid, threads, 0, s>>>((const uint4*)x1, c1, (const uint4*)x2, c2, stats, gamma, beta, \
-                                                  (uint4*)out, hw, groups, appb)
+  SDXE_CUDA_CHECK(launch_k(gn_apply_kernel<B, S>, agrid, dim3(threads), 0, s, (const uint4*)x1, c1, (const uint4*)x2, c2, \
+                           (const float*)stats, gamma, beta, (uint4*)out, hw, groups, appb))
   if (bf16) { if (silu) GN_APPLY(true, true); else GN_APPLY(true, false); }
   else { if (silu) GN_APPLY(false, true); else GN_APPLY(false, false); }
 #undef GN_APPLY
@@ -312,6 +320,8 @@ int group_norm_launch(const void* x1, int c1, const void* x2, int c2, const floa
 template <bool BF16, int MAXV>  // MAXV x 32 x 8 channels held in registers (one global read of the row)
 __global__ void __launch_bounds__(256) layer_norm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, uint4* __restrict__ out, int rows, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int V = C >> 3;
@@ -363,6 +373,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const uint4* __restrict
 template <bool BF16, int G>
 __global__ void __launch_bounds__(256) layer_norm5_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, uint4* __restrict__ out, int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int RPW = 32 / G, V = 5 * G, C = 8 * V;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int row = warp * RPW + lane / G, gl = lane % G;
@@ -414,7 +426,7 @@ int layer_norm_launch(const void* x, const float* gamma, const float* beta, void
   if (c == 320 || c == 640 || c == 1280) {
     const int G = c / 40, rpb = 8 * (32 / G);  // rows per 256-thread block
     const int nb = (rows + rpb - 1) / rpb;
-#define LN5(B, GG) layer_norm5_kernel<B, GG><<<nb, 256, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, eps)
+#define LN5(B, GG) SDXE_CUDA_CHECK(launch_k(layer_norm5_kernel<B, GG>, dim3(nb), dim3(256), 0, s, (const uint4*)x, gamma, beta, (uint4*)out, rows, eps))
     if (bf16) { if (G == 8) LN5(true, 8); else if (G == 16) LN5(true, 16); else LN5(true, 32); }
     else { if (G == 8) LN5(false, 8); else if (G == 16) LN5(false, 16); else LN5(false, 32); }
 #undef LN5
@@ -423,7 +435,7 @@ int layer_norm_launch(const void* x, const float* gamma, const float* beta, void
   }
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per block
   const int nv = (c / 8 + 31) / 32;   // vectors per lane
-#define LN_LAUNCH(B, MV) layer_norm_kernel<B, MV><<<blocks, 256, 0, s>>>((const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps)
+#define LN_LAUNCH(B, MV) SDXE_CUDA_CHECK(launch_k(layer_norm_kernel<B, MV>, dim3(blocks), dim3(256), 0, s, (const uint4*)x, gamma, beta, (uint4*)out, rows, c, eps))
   if (bf16) { if (nv <= 2) LN_LAUNCH(true, 2); else if (nv <= 3) LN_LAUNCH(true, 3); else if (nv <= 5) LN_LAUNCH(true, 5); else LN_LAUNCH(true, 8); }
   else { if (nv <= 2) LN_LAUNCH(false, 2); else if (nv <= 3) LN_LAUNCH(false, 3); else if (nv <= 5) LN_LAUNCH(false, 5); else LN_LAUNCH(false, 8); }
 #undef LN_LAUNCH
@@ -436,6 +448,8 @@ int layer_norm_launch(const void* x, const float* gamma, const float* beta, void
 // =============================================================================================================
 __global__ void im2col3x3_kernel(const uint4* __restrict__ x, uint4* __restrict__ A, int n, int H, int W, int C, int Ho,
                                  int Wo, int stride, int pad_lo, int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int KV = kpad >> 3;
   const size_t total = (size_t)n * Ho * Wo * KV;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -461,7 +475,7 @@ int im2col3x3_launch(const void* x, void* A, int n, int H, int W, int C, int Ho,
   if (C % 8 || kpad % 8) { set_last_error(__FILE__, __LINE__, "im2col: alignment"); return -1; }
   const size_t total = (size_t)n * Ho * Wo * (kpad / 8);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
-  im2col3x3_kernel<<<blocks, 256, 0, s>>>((const uint4*)x, (uint4*)A, n, H, W, C, Ho, Wo, stride, pad_lo, kpad);
+  SDXE_CUDA_CHECK(launch_k(im2col3x3_kernel, dim3(blocks), dim3(256), 0, s, (const uint4*)x, (uint4*)A, n, H, W, C, Ho, Wo, stride, pad_lo, kpad));
   SDXE_LAUNCH_CHECK();
   return 0;
 }
@@ -502,6 +516,8 @@ int im2col3x3_nchw_launch(const void* x, int io_dtype, void* A, int n, int C, in
 }
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int H, int W, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)n * 2 * H * 2 * W * V;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int v = (int)(idx % V);
@@ -517,7 +533,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 int upsample2x_launch(const void* x, void* out, int n, int H, int W, int C, cudaStream_t s) {
   const size_t total = (size_t)n * 4 * H * W * (C / 8);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
-  upsample2x_kernel<<<blocks, 256, 0, s>>>((const uint4*)x, (uint4*)out, n, H, W, C / 8);
+  SDXE_CUDA_CHECK(launch_k(upsample2x_kernel, dim3(blocks), dim3(256), 0, s, (const uint4*)x, (uint4*)out, n, H, W, C / 8));
   SDXE_LAUNCH_CHECK();
   return 0;
 }
@@ -595,6 +611,8 @@ template <bool BF16, int MT, int NPW>
 __global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, const uint4* __restrict__ W,
                                      const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ out,
                                      int ldo, int M, int N, int K, int silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n0 = warp * NPW;
   if (n0 >= N) return;
@@ -652,9 +670,9 @@ int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b
   const int warps = (N + NPW - 1) / NPW;
   const int blocks = (warps + 3) / 4;
   if (bf16)
-    skinny_linear_kernel<true, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0);
+    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<true, MT, NPW>, dim3(blocks), dim3(128), 0, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
   else
-    skinny_linear_kernel<false, MT, NPW><<<blocks, 128, 0, s>>>(in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0);
+    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<false, MT, NPW>, dim3(blocks), dim3(128), 0, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
   SDXE_LAUNCH_CHECK();
   return 0;
 }

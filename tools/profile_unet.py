@@ -58,6 +58,10 @@ y = torch.randn(n, spec.adm_in_channels, device=dev, dtype=dt) if spec.adm_in_ch
 if args.profile:
     eng.forward(x, t, ctx, y)
     eng.profile(True)
+if not args.profile:
+    for _ in range(2):  # plan build + graph capture happen on the first call of a shape
+        eng.forward(x, t, ctx, y)
+    torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 for _ in range(args.iters):
