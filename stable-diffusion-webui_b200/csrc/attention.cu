@@ -325,6 +325,7 @@ int attention_init() {
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (attention2_init() != 0) return -1;
+    if (attentionx_init() != 0) return -1;
     done = true;
   }
   return 0;
@@ -336,6 +337,9 @@ int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
     // SDXE_ATTN: 2 = attention2 (two Q tiles per CTA) where eligible [default], 1 = this file's kernel only
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("SDXE_ATTN"); mode = e ? atoi(e) : 2; }
+    static int usex = -1;  // SDXE_ATTNX=0: keep short-KV (cross-) attention on the general kernels
+    if (usex < 0) { const char* e = getenv("SDXE_ATTNX"); usex = e ? atoi(e) : 1; }
+    if (usex && attentionx_eligible(a)) return attentionx_launch(a, bf16, stream);
     if (mode == 2 && attention2_eligible(a)) return attention2_launch(a, bf16, stream);
   }
   if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {

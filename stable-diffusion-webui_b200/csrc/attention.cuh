@@ -27,5 +27,9 @@ int attention_init();
 bool attention2_eligible(const AttnArgs& a);
 int attention2_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
 int attention2_init();
+// persistent, software-pipelined short-KV (cross-) attention: Nk <= 128, head dim <= 64 (attention_x.cu)
+bool attentionx_eligible(const AttnArgs& a);
+int attentionx_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
+int attentionx_init();
 
 }  // namespace sdxe

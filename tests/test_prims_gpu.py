@@ -90,6 +90,9 @@ def test_conv3x3(cuda, dtype, n, h, w, cin, cout):
     (1, 1, 128, 128, 64), (2, 2, 256, 256, 64), (2, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (2, 8, 1024, 77, 80),
     (2, 8, 256, 256, 160), (2, 8, 64, 64, 160), (2, 8, 64, 77, 160), (1, 10, 4096, 154, 64), (1, 20, 1024, 1024, 64),
     (1, 1, 1024, 1024, 512), (1, 1, 4096, 4096, 512), (1, 2, 200, 333, 64), (1, 1, 128, 300, 128),
+    # short-KV persistent kernel (Nk <= 128, D <= 64): more items than SMs, ragged Nq, every key-count class
+    (2, 8, 4096, 77, 40), (2, 10, 1024, 77, 64), (1, 3, 200, 77, 40), (1, 2, 128, 128, 64), (1, 2, 384, 100, 48),
+    (1, 1, 64, 16, 8), (3, 5, 130, 1, 32), (16, 8, 4096, 77, 40),
 ])
 def test_attention(cuda, dtype, B, H, Nq, Nk, D):
     from sdwebui_b200 import ops
