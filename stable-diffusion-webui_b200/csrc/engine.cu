@@ -53,6 +53,7 @@ struct LinW {  // 16-bit [N, ld] K-contiguous (+ fp32 bias)
   int N = 0, K = 0, ld = 0;
   int Nrows = 0;  // rows allocated (N rounded up to 16, zero filled) so a TMA box never exceeds the tensor
   int geglu_tile = 0;
+  float* c1 = nullptr;  // LayerNorm folded in (gemm.cuh): row sums of the gamma-scaled weight; b then includes beta W^T
 };
 struct NormW {
   float* g = nullptr;
@@ -165,6 +166,7 @@ struct sdxe_engine {
   int pack_linear(LinW& out, const std::vector<std::string>& wkeys, const std::vector<std::string>& bkeys, int n_each, int K,
                   int mode, int kpad = 0, int geglu_tile = 0);
   int pack_norm(NormW& out, const std::string& prefix, int C);
+  int fold_layer_norm(LinW& w, const NormW& ln);  // w consumes LayerNorm(ln) output: fold gamma / beta into w
   int pack_f32(float*& out, const std::string& key, int64_t n);
   int build_unet();
   int build_vae();
@@ -230,6 +232,15 @@ struct Builder {
     a.p = nullptr;
   }
 
+  struct RowStats {  // per-row partial (sum, sum of squares) of an activation, [parts][M] float2
+    Buf buf;
+    const float2* p = nullptr;
+    int parts = 0;
+  };
+  void free_stats(RowStats& st) {
+    if (st.buf.p) e->release(st.buf);
+    st.p = nullptr; st.parts = 0;
+  }
   // out[M, N] = A (+A2) * W^T with the fused epilogues of gemm.cu
   struct GemmOpt {
     const void* A2 = nullptr;
@@ -240,6 +251,11 @@ struct Builder {
     int ldr = 0;
     int epi = EPI_PLAIN;
     int ldo = 0;
+    // LayerNorm fold (gemm.cuh): statistics of the A rows as emitted by the GEMM that produced A
+    const float2* ln_part = nullptr;
+    int ln_parts = 0;
+    // emit per-row partial statistics of the output for a following folded LayerNorm: filled in by gemm()
+    RowStats* emit = nullptr;
   };
   int gemm(const void* A, int lda, int64_t M, const LinW& W, void* out, const GemmOpt& o) {
     GemmArgs a;
@@ -256,6 +272,18 @@ struct Builder {
     a.residual = o.residual; a.ldr = o.ldr;
     a.out = out;
     a.ldo = o.ldo ? o.ldo : (o.epi == EPI_GEGLU ? W.N / 2 : (W.N + 7) / 8 * 8);
+    if (W.c1) {  // this weight has a LayerNorm folded in: it can only be applied with the row statistics of A
+      if (!o.ln_part || o.A2) EFAIL("gemm: folded LayerNorm weight without row statistics");
+      a.c1 = W.c1; a.ln_part = o.ln_part; a.ln_parts = o.ln_parts;
+      a.ln_inv_c = 1.0f / (float)W.K; a.ln_eps = 1e-5f;
+    }
+    if (o.emit) {
+      const int num_n = (a.N + a.BN - 1) / a.BN;
+      o.emit->buf = e->alloc((size_t)2 * num_n * M * sizeof(float2));
+      o.emit->p = (const float2*)o.emit->buf.p;
+      o.emit->parts = 2 * num_n;
+      a.stat_out = (float2*)o.emit->buf.p;
+    }
     ECHK(gemm_finish_args(a, W.w, std::max(W.N, W.Nrows), W.ld));
     const bool b = bf16;
     const double nout = (o.epi == EPI_GEGLU) ? W.N / 2.0 : (double)W.N;
@@ -416,48 +444,61 @@ struct Builder {
     Act xn;
     ECHK(group_norm(x, nullptr, st.gn, 1e-6f, false, xn));
     Act h = new_act(x.n, x.h, x.w, C);
-    ECHK(gemm(xn.p, C, M, st.proj_in, h.p, GemmOpt()));
+    // The three LayerNorms of a block are folded into the GEMMs that consume them: the GEMM that PRODUCES the token
+    // stream h also emits each row's (sum, sum of squares), the consumer's epilogue normalises with them.
+    RowStats hs;
+    {
+      GemmOpt oi;
+      oi.emit = &hs;
+      ECHK(gemm(xn.p, C, M, st.proj_in, h.p, oi));
+    }
     free_act(xn);
-    for (const TBlockW& tb : st.blocks) {
-      // --- self attention
-      Act ln = new_act(x.n, x.h, x.w, C);
-      ECHK(layer_norm(h.p, M, tb.ln1, ln.p));
+    for (size_t bi = 0; bi < st.blocks.size(); ++bi) {
+      const TBlockW& tb = st.blocks[bi];
+      const bool last = bi + 1 == st.blocks.size();
+      // --- self attention: q | k | v = LN1(h) W^T
       Act qkv = new_act(x.n, x.h, x.w, 3 * C);
-      ECHK(gemm(ln.p, C, M, tb.qkv1, qkv.p, GemmOpt()));  // columns: [q | k | v], heads contiguous inside each
+      GemmOpt oq;
+      oq.ln_part = hs.p; oq.ln_parts = hs.parts;
+      ECHK(gemm(h.p, C, M, tb.qkv1, qkv.p, oq));  // columns: [q | k | v], heads contiguous inside each
+      free_stats(hs);
       Act att = new_act(x.n, x.h, x.w, C);
       const uint16_t* qkv16 = (const uint16_t*)qkv.p;
       ECHK(attention(qkv16, qkv16 + C, qkv16 + 2 * C, B, H, tokens, tokens, dh, 3 * C, 3 * C, scale, att.p, C, dh));
       free_act(qkv);
       Act h2 = new_act(x.n, x.h, x.w, C);
       GemmOpt oo;
-      oo.residual = h.p; oo.ldr = C;
+      oo.residual = h.p; oo.ldr = C; oo.emit = &hs;
       ECHK(gemm(att.p, C, M, tb.out1, h2.p, oo));
       free_act(h);
       h = h2;
-      // --- cross attention
-      ECHK(layer_norm(h.p, M, tb.ln2, ln.p));
+      // --- cross attention: q = LN2(h) W^T
       Act q2 = new_act(x.n, x.h, x.w, C);
-      ECHK(gemm(ln.p, C, M, tb.q2, q2.p, GemmOpt()));
+      GemmOpt oq2;
+      oq2.ln_part = hs.p; oq2.ln_parts = hs.parts;
+      ECHK(gemm(h.p, C, M, tb.q2, q2.p, oq2));
+      free_stats(hs);
       const uint16_t* kv = (const uint16_t*)kv_all + tb.kv_off;  // columns: [k | v] of this block
       ECHK(attention(q2.p, kv, kv + C, B, H, tokens, ctx_len, dh, C, ld_kv, scale, att.p, C, dh));
       free_act(q2);
       Act h3 = new_act(x.n, x.h, x.w, C);
       GemmOpt oo2;
-      oo2.residual = h.p; oo2.ldr = C;
+      oo2.residual = h.p; oo2.ldr = C; oo2.emit = &hs;
       ECHK(gemm(att.p, C, M, tb.out2, h3.p, oo2));
       free_act(att);
       free_act(h);
       h = h3;
-      // --- feed forward (GEGLU fused into the first GEMM's epilogue)
-      ECHK(layer_norm(h.p, M, tb.ln3, ln.p));
+      // --- feed forward: GEGLU(LN3(h)) fused into the first GEMM's epilogue
       Act ff = new_act(x.n, x.h, x.w, 4 * C);
       GemmOpt og;
       og.epi = EPI_GEGLU;
-      ECHK(gemm(ln.p, C, M, tb.ff1, ff.p, og));
-      free_act(ln);
+      og.ln_part = hs.p; og.ln_parts = hs.parts;
+      ECHK(gemm(h.p, C, M, tb.ff1, ff.p, og));
+      free_stats(hs);
       Act h4 = new_act(x.n, x.h, x.w, C);
       GemmOpt of;
       of.residual = h.p; of.ldr = C;
+      if (!last) of.emit = &hs;  // the next block's LN1
       ECHK(gemm(ff.p, 4 * C, M, tb.ff2, h4.p, of));
       free_act(ff);
       free_act(h);
@@ -573,6 +614,19 @@ int sdxe_engine::pack_norm(NormW& out, const std::string& prefix, int C) {
   }
   return 0;
 }
+int sdxe_engine::fold_layer_norm(LinW& w, const NormW& ln) {
+  if (ln.C != w.K) EFAIL("fold_layer_norm: width mismatch");
+  const size_t nb = align_up((size_t)w.N, 8);
+  const bool had_bias = w.b != nullptr;
+  if (!had_bias) w.b = alloc32(nb);
+  w.c1 = alloc32(nb);
+  if (!sizing) {
+    if (!had_bias) SDXE_CUDA_CHECK(cudaMemsetAsync(w.b, 0, nb * 4, 0));
+    SDXE_CUDA_CHECK(cudaMemsetAsync(w.c1, 0, nb * 4, 0));
+    ECHK(ln_fold_launch(w.w, w.N, w.K, w.ld, ln.g, ln.b, w.b, w.c1, bf16, 0));
+  }
+  return 0;
+}
 int sdxe_engine::pack_f32(float*& out, const std::string& key, int64_t n) {
   out = alloc32(n);
   const RawWeight* w = find(key, n);
@@ -625,6 +679,10 @@ int sdxe_engine::build_st(STW& s, const std::string& p, int C, int depth) {
     const int tile = n1 % 256 == 0 ? 256 : (n1 % 128 == 0 ? 128 : 64);
     ECHK(pack_linear(t.ff1, {b + ".ff.net.0.proj.weight"}, {b + ".ff.net.0.proj.bias"}, n1, C, PACK_GEGLU, 0, tile));
     ECHK(pack_linear(t.ff2, {b + ".ff.net.2.weight"}, {b + ".ff.net.2.bias"}, C, 4 * C, PACK_PLAIN));
+    // norm1 / norm2 / norm3 are folded into the GEMMs that consume them (no LayerNorm kernel runs)
+    ECHK(fold_layer_norm(t.qkv1, t.ln1));
+    ECHK(fold_layer_norm(t.q2, t.ln2));
+    ECHK(fold_layer_norm(t.ff1, t.ln3));
   }
   return 0;
 }

@@ -29,14 +29,14 @@ static constexpr int BLOCK_K = 64;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 static constexpr int TMEM_COLS = 512;
-static constexpr int SBIAS_BYTES = 2 * 256 * 4;  // per-tile bias slice in smem, double buffered
+static constexpr int SBIAS_BYTES = 4 * 256 * 4;  // per-tile bias and LayerNorm-fold c1 slices in smem, double buffered
 static constexpr int CHUNK_BYTES = 32 * 32 * 2;   // one epilogue chunk: 32 rows x 32 columns, 16 bit
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int NUM_BARS_FIXED = 4 + 2 * NUM_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][2]
 
 // EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
-template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER>
+template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER, bool LNF, bool STAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -244,7 +244,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       const bool row_ok = m < M;
       const int n_out0 = n_blk * out_cols;  // first output column of this tile
       float* sb = sbias + (tile_ctr & 1u) * 256;
-      for (int j = et; j < BN; j += 256) sb[j] = (biasp != nullptr && n_blk * BN + j < N) ? __ldg(biasp + n_blk * BN + j) : 0.f;
+      float* sc = sbias + 512 + (tile_ctr & 1u) * 256;  // LayerNorm fold: c1 of this tile's columns
+      for (int j = et; j < BN; j += 256) {
+        const bool in = n_blk * BN + j < N;
+        sb[j] = (biasp != nullptr && in) ? __ldg(biasp + n_blk * BN + j) : 0.f;
+        if (LNF) sc[j] = in ? __ldg(a.c1 + n_blk * BN + j) : 0.f;
+      }
+      float ln_mu = 0.f, ln_rs = 1.f;
+      if (LNF) {  // this row's mean / rstd from the producer's partial sums (fixed order: deterministic)
+        float ps = 0.f, pq = 0.f;
+        if (row_ok) {
+          for (int pp = 0; pp < a.ln_parts; ++pp) {
+            const float2 t = __ldg(a.ln_part + (size_t)pp * M + m);
+            ps += t.x;
+            pq += t.y;
+          }
+        }
+        ln_mu = ps * a.ln_inv_c;
+        ln_rs = rsqrtf(fmaxf(pq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
+      }
+      float st_s = 0.f, st_q = 0.f;  // STAT: this thread's share of its row's (sum, sum of squares)
       auto res_load = [&](int c0, uint32_t ctr) {  // elected lane: residual chunk -> staging buffer ctr & 1
         const uint32_t b = ctr & 1u;
         const int nc = min(32, out_cols - c0);
@@ -298,16 +317,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
             {
               const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + c0 + g + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              if (LNF) {
+                const float4 k0 = *reinterpret_cast<const float4*>(sc + c0 + g), k1 = *reinterpret_cast<const float4*>(sc + c0 + g + 4);
+                v[0] = fmaf(ln_rs, v[0] - ln_mu * k0.x, b0.x); v[1] = fmaf(ln_rs, v[1] - ln_mu * k0.y, b0.y);
+                v[2] = fmaf(ln_rs, v[2] - ln_mu * k0.z, b0.z); v[3] = fmaf(ln_rs, v[3] - ln_mu * k0.w, b0.w);
+                v[4] = fmaf(ln_rs, v[4] - ln_mu * k1.x, b1.x); v[5] = fmaf(ln_rs, v[5] - ln_mu * k1.y, b1.y);
+                v[6] = fmaf(ln_rs, v[6] - ln_mu * k1.z, b1.z); v[7] = fmaf(ln_rs, v[7] - ln_mu * k1.w, b1.w);
+              } else {
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
             }
             if (GEGLU) {
               const float4 b0 = *reinterpret_cast<const float4*>(sb + half + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + half + c0 + g + 4);
               float gt[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(rg[(GEGLU ? g : 0) + (GEGLU ? j : 0)]);
+              if (LNF) {
+                const float4 k0 = *reinterpret_cast<const float4*>(sc + half + c0 + g), k1 = *reinterpret_cast<const float4*>(sc + half + c0 + g + 4);
+                gt[0] = fmaf(ln_rs, gt[0] - ln_mu * k0.x, b0.x); gt[1] = fmaf(ln_rs, gt[1] - ln_mu * k0.y, b0.y);
+                gt[2] = fmaf(ln_rs, gt[2] - ln_mu * k0.z, b0.z); gt[3] = fmaf(ln_rs, gt[3] - ln_mu * k0.w, b0.w);
+                gt[4] = fmaf(ln_rs, gt[4] - ln_mu * k1.x, b1.x); gt[5] = fmaf(ln_rs, gt[5] - ln_mu * k1.y, b1.y);
+                gt[6] = fmaf(ln_rs, gt[6] - ln_mu * k1.z, b1.z); gt[7] = fmaf(ln_rs, gt[7] - ln_mu * k1.w, b1.w);
+              } else {
               gt[0] += b0.x; gt[1] += b0.y; gt[2] += b0.z; gt[3] += b0.w;
               gt[4] += b1.x; gt[5] += b1.y; gt[6] += b1.z; gt[7] += b1.w;
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] *= gelu_fast_f(gt[j]);
             }
@@ -340,6 +375,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             packed[g >> 3].y = T16<BF16>::pack(v[2], v[3]);
             packed[g >> 3].z = T16<BF16>::pack(v[4], v[5]);
             packed[g >> 3].w = T16<BF16>::pack(v[6], v[7]);
+            if (STAT) {  // statistics of the values as stored (rounded to 16 bit), like a LayerNorm reading them back
+              const uint4 pk = packed[g >> 3];
+              float2 f;
+              f = T16<BF16>::unpack(pk.x); st_s += f.x + f.y; st_q = fmaf(f.x, f.x, fmaf(f.y, f.y, st_q));
+              f = T16<BF16>::unpack(pk.y); st_s += f.x + f.y; st_q = fmaf(f.x, f.x, fmaf(f.y, f.y, st_q));
+              f = T16<BF16>::unpack(pk.z); st_s += f.x + f.y; st_q = fmaf(f.x, f.x, fmaf(f.y, f.y, st_q));
+              f = T16<BF16>::unpack(pk.w); st_s += f.x + f.y; st_q = fmaf(f.x, f.x, fmaf(f.y, f.y, st_q));
+            }
           }
         }
         if (!RES) {
@@ -365,6 +408,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         }
         __syncwarp();
       }
+      if (STAT && row_ok) a.stat_out[(size_t)(n_blk * 2 + ehalf) * M + m] = make_float2(st_s, st_q);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -416,7 +460,7 @@ int gemm_pick_stages(int BN, bool residual) {
   return std::max(2, std::min(s, 8));
 }
 int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld) {
-  a.cluster = gemm_pick_cluster(a.M, a.BN);
+  a.cluster = (a.c1 || a.stat_out) ? 1 : gemm_pick_cluster(a.M, a.BN);  // fold / statistics variants are un-paired only
   const int bn_cta = a.cluster == 2 ? a.BN / 2 : a.BN;
   a.num_stages = gemm_pick_stages(bn_cta, a.residual != nullptr);
   if (make_tmap_2d(&a.tmB, W, w_rows, a.K, w_ld, bn_cta)) return -1;
@@ -454,18 +498,30 @@ int gemm_pick_bn(int M, int N, int K, int epi) {
 }
 
 typedef void (*GemmKernel)(const GemmArgs);
-// variant index = cluster * 10 + bf16 * 5 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu}
+// variant index = cluster * 10 + bf16 * 5 + {0: plain, 1: plain+res, 2: plain+rowvec, 3: plain+res+rowvec, 4: geglu};
+// un-paired only: 20 + bf16 * 4 + {0: plain+lnfold, 1: geglu+lnfold, 2: plain+stat, 3: plain+res+stat}
 template <bool BF16, bool CL>
 static GemmKernel gemm_variant_e(int e) {
   switch (e) {
-    case 0: return gemm_kernel<BF16, EPI_PLAIN, false, false, CL>;
-    case 1: return gemm_kernel<BF16, EPI_PLAIN, true, false, CL>;
-    case 2: return gemm_kernel<BF16, EPI_PLAIN, false, true, CL>;
-    case 3: return gemm_kernel<BF16, EPI_PLAIN, true, true, CL>;
-    default: return gemm_kernel<BF16, EPI_GEGLU, false, false, CL>;
+    case 0: return gemm_kernel<BF16, EPI_PLAIN, false, false, CL, false, false>;
+    case 1: return gemm_kernel<BF16, EPI_PLAIN, true, false, CL, false, false>;
+    case 2: return gemm_kernel<BF16, EPI_PLAIN, false, true, CL, false, false>;
+    case 3: return gemm_kernel<BF16, EPI_PLAIN, true, true, CL, false, false>;
+    default: return gemm_kernel<BF16, EPI_GEGLU, false, false, CL, false, false>;
   }
 }
+template <bool BF16>
+static GemmKernel gemm_variant_x(int e) {
+  switch (e) {
+    case 0: return gemm_kernel<BF16, EPI_PLAIN, false, false, false, true, false>;
+    case 1: return gemm_kernel<BF16, EPI_GEGLU, false, false, false, true, false>;
+    case 2: return gemm_kernel<BF16, EPI_PLAIN, false, false, false, false, true>;
+    default: return gemm_kernel<BF16, EPI_PLAIN, true, false, false, false, true>;
+  }
+}
+static constexpr int GEMM_NUM_VARIANTS = 28;
 static GemmKernel gemm_variant(int i) {
+  if (i >= 20) return (i - 20) / 4 ? gemm_variant_x<true>((i - 20) % 4) : gemm_variant_x<false>((i - 20) % 4);
   const int cl = i / 10, bf = (i % 10) / 5, e = i % 5;
   if (cl) return bf ? gemm_variant_e<true, true>(e) : gemm_variant_e<false, true>(e);
   return bf ? gemm_variant_e<true, false>(e) : gemm_variant_e<false, false>(e);
@@ -474,7 +530,7 @@ static GemmKernel gemm_variant(int i) {
 int gemm_init() {
   static bool done = false;
   if (!done) {
-    for (int i = 0; i < 20; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < GEMM_NUM_VARIANTS; ++i) SDXE_CUDA_CHECK(cudaFuncSetAttribute(gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done = true;
   }
   return 0;
@@ -498,6 +554,14 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   const int vi = a.epi == EPI_GEGLU ? 4 : ((a.residual ? 1 : 0) | (a.rowvec ? 2 : 0));
   if ((a.epi != EPI_PLAIN) && (a.residual || a.rowvec)) { set_last_error(__FILE__, __LINE__, "gemm: residual / rowvec need EPI_PLAIN"); return -1; }
   GemmKernel kern = gemm_variant(vi + (bf16 ? 5 : 0) + (a.cluster == 2 ? 10 : 0));
+  if (a.c1 || a.stat_out) {
+    if (a.cluster == 2 || a.rowvec || (a.c1 && (a.residual || a.stat_out)) || (a.stat_out && a.epi != EPI_PLAIN)) {
+      set_last_error(__FILE__, __LINE__, "gemm: unsupported LayerNorm-fold / statistics combination");
+      return -1;
+    }
+    const int xi = a.c1 ? (a.epi == EPI_GEGLU ? 1 : 0) : (a.residual ? 3 : 2);
+    kern = gemm_variant(20 + (bf16 ? 4 : 0) + xi);
+  }
   if (gemm_init() != 0) return -1;
   if (a.cluster == 2) {
     cudaLaunchConfig_t cfg;

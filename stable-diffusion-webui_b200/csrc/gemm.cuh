@@ -36,6 +36,15 @@ struct alignas(64) GemmArgs {
   const void* residual;  // [M, ldr] 16-bit or null
   void* out;             // [M, ldo] 16-bit
   int ldo;
+  // LayerNorm folded into this GEMM (A is the UN-normalised activation, W already carries gamma):
+  //   out[m, n] = rstd[m] * (acc[m, n] - mean[m] * c1[n]) + bias[n]      c1[n] = sum_k W'[n, k], bias includes beta W^T
+  // mean / rstd of row m come from the per-row partial (sum, sum of squares) the PRODUCING GEMM wrote (stat_out there).
+  const float* c1;          // [N] (GEGLU: interleaved like the bias) or null = no fold
+  const float2* ln_part;    // [ln_parts][M] partial (sum, sumsq) of the A rows
+  int ln_parts;
+  float ln_inv_c, ln_eps;   // 1 / K (the normalised width), epsilon
+  // emit per-row partial statistics of the (rounded) output for a consumer's LayerNorm fold:
+  float2* stat_out;         // [2 * num_n][M]: part (n_blk * 2 + warp half); null = off. Needs EPI_PLAIN, no rowvec.
 };
 
 // Launch on `stream`. bf16 selects the 16-bit format of A/B/out/residual. Returns 0 / -1.

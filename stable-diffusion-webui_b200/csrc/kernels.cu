@@ -753,6 +753,43 @@ int pack_vector_launch(const void* src, int src_dtype, float* dst, int n, int ge
   return 0;
 }
 
+// LayerNorm folded into the consuming GEMM (gemm.cuh): per output row n of a packed weight [rows, ld]
+//   bias'[n] = bias[n] + sum_k beta[k] W[n, k];  W'[n, k] = round16(W[n, k] * gamma[k]) (in place);  c1[n] = sum_k W'[n, k]
+// Row interleaving (GEGLU packing) is irrelevant: gamma / beta run along K, bias / c1 are indexed like the packed rows.
+template <bool BF16>
+__global__ void ln_fold_kernel(typename T16<BF16>::type* __restrict__ w, int rows, int K, int ld,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ bias,
+                               float* __restrict__ c1) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= rows) return;
+  typename T16<BF16>::type* wr = w + (size_t)n * ld;
+  float sb = 0.f, sc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = T16<BF16>::to_f(wr[k]);
+    sb = fmaf(beta[k], wv, sb);
+    const typename T16<BF16>::type wf = T16<BF16>::from_f(wv * gamma[k]);
+    wr[k] = wf;
+    sc += T16<BF16>::to_f(wf);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if (lane == 0) {
+    bias[n] += sb;
+    c1[n] = sc;
+  }
+}
+int ln_fold_launch(void* w, int rows, int K, int ld, const float* gamma, const float* beta, float* bias, float* c1, bool bf16,
+                   cudaStream_t s) {
+  const int blocks = (rows * 32 + 255) / 256;
+  if (bf16) ln_fold_kernel<true><<<blocks, 256, 0, s>>>((__nv_bfloat16*)w, rows, K, ld, gamma, beta, bias, c1);
+  else ln_fold_kernel<false><<<blocks, 256, 0, s>>>((__half*)w, rows, K, ld, gamma, beta, bias, c1);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
 // =============================================================================================================
 // sampler-step fusions (latents stay fp32, as in the reference: x comes from torch.randn fp32, modules/rng.py:19)
 // =============================================================================================================

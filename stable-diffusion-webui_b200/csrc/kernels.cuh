@@ -42,6 +42,10 @@ enum : int { PACK_PLAIN = 0, PACK_CONV3 = 1, PACK_GEGLU = 2 };
 // GEGLU: PLAIN with rows permuted so that every `tile` rows hold tile/2 value rows then the matching gate rows.
 int pack_weight_launch(const void* src, int src_dtype, void* dst, int mode, int rows, int cols, int ld, int tile,
                        bool bf16, cudaStream_t s);
+// fold a LayerNorm's affine into the packed weight that consumes its output (see gemm.cuh); bias must be allocated (zeroed if the
+// layer has none), c1 receives the row sums of the folded weight
+int ln_fold_launch(void* w, int rows, int K, int ld, const float* gamma, const float* beta, float* bias, float* c1, bool bf16,
+                   cudaStream_t s);
 int pack_vector_launch(const void* src, int src_dtype, float* dst, int n, int geglu_tile, bool round16, bool bf16,
                        cudaStream_t s);
 
