@@ -366,7 +366,9 @@ def main():
             traffic, traffic_src = tj["traffic_per_launch_bytes"], tj["source"]
         roofline = {"bound": "tensor", "kernel": "sdxe::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved,
                     "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                    "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)", "traffic": None,
+                    "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)", "traffic": traffic,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": (prof_u["gemm"]["bytes"] + prof_u["conv3x3"]["bytes"]) / max(1, mm_n),
                     "launches_per_unet_call": mm_n, "avg_launch_us": 1000.0 * mm_ms / max(1, mm_n),
                     "share_of_unet_call": mm_ms / total_u if total_u else None,
                     "how": "CUDA events around every launch of one extra instrumented UNet call on the launching stream "
