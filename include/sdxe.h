@@ -34,7 +34,7 @@ extern "C" {
 /* 16-bit storage / compute input format of activations and weights (accumulation is always fp32). */
 enum sdxe_dtype { SDXE_F16 = 0, SDXE_BF16 = 1, SDXE_F32 = 2 };
 
-enum sdxe_model_kind { SDXE_MODEL_UNET = 0, SDXE_MODEL_VAE_DECODER = 1 };
+enum sdxe_model_kind { SDXE_MODEL_UNET = 0, SDXE_MODEL_VAE_DECODER = 1, SDXE_MODEL_VAE_ENCODER = 2 };
 
 #define SDXE_MAX_LEVELS 8
 
@@ -92,6 +92,11 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
                       int n, int h, int w, int ctx_len, int io_dtype, void* stream);
 /* image = AutoencoderKL.decode(z): z [n, 4, h, w] (already divided by scale_factor) -> [n, 3, 8h, 8w] NCHW. */
 int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int w, int io_dtype, void* stream);
+/* moments = quant_conv(AutoencoderKL.encoder(x)): x [n, 3, H, W] in [-1, 1] NCHW -> [n, 2*z_channels, H/8, W/8]
+ * (mean | logvar, the input of DiagonalGaussianDistribution). Replaces model.encode_first_stage(image) in
+ * modules/sd_samplers_common.py:87-112 (images_tensor_to_samples), used by img2img init (modules/processing.py:1602-1757).
+ * Engine kind SDXE_MODEL_VAE_ENCODER, weights "encoder.*" and "quant_conv.*". H, W multiples of 2^(num_levels-1) (8). */
+int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int w, int io_dtype, void* stream);
 
 /* Per-kernel-class timing: while enabled, forward / decode calls run their plan eagerly with a CUDA event pair
  * around every launch on the launching stream. kind: 0 GEMM (tcgen05), 1 conv3x3 implicit GEMM (tcgen05),

@@ -154,10 +154,15 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None):
     return x
 
 
-def setup_img2img_steps(steps_requested: int, denoising_strength: float):
-    """modules/sd_samplers_common.py:22-31 with `steps` given (the hires second pass)."""
-    steps = int(steps_requested / min(denoising_strength, 0.999)) if denoising_strength > 0 else 0
-    t_enc = steps_requested - 1
+def setup_img2img_steps(steps_requested: int, denoising_strength: float, steps_given: bool = True):
+    """modules/sd_samplers_common.py:22-31. `steps_given` = the caller passed `steps` (the hires second pass does,
+    :25-27); plain img2img does not and, with img2img_fix_steps off (the default), takes the else branch (:28-30)."""
+    if steps_given:
+        steps = int(steps_requested / min(denoising_strength, 0.999)) if denoising_strength > 0 else 0
+        t_enc = steps_requested - 1
+    else:
+        steps = steps_requested
+        t_enc = int(min(denoising_strength, 0.999) * steps)
     return steps, t_enc
 
 

@@ -85,6 +85,38 @@ class OraclePipeline:
         xi = samples + noise * sigma_sched[0]
         return self._run_sampler(p, xi, sigma_sched, rng2, cond, uncond, y_cond, y_uncond)
 
+    # -- img2img: modules/processing.py:1728-1790, latent path ------------------------------------------
+    @torch.no_grad()
+    def img2img(self, p: SamplingParams, encoder, init_images, cond, uncond, encode_noise=None, latent_mask=None,
+                y_cond=None, y_uncond=None):
+        """init_images [B,3,H,W] in [0,1]; encoder = vae.AutoencoderKLEncode. -> final latent fp32."""
+        from .vae import gaussian_sample
+
+        x = init_images.to(self.device, self.dtype_vae) * 2 - 1
+        lat = torch.cat([gaussian_sample(encoder.encode_moments(x[i:i + 1]),
+                                         None if encode_noise is None else encode_noise[i:i + 1]) for i in range(x.shape[0])])
+        init_latent = p.scale_factor * lat.float()
+        shape = (4, p.height // 8, p.width // 8)
+        rng = ImageRNG(shape, p.seeds, source=p.randn_source, device=self.device)
+        noise = rng.next()
+        steps, t_enc = K.setup_img2img_steps(p.steps, p.denoising_strength, steps_given=False)
+        sig = K.webui_sigmas(self.model_wrap, p.sampler, steps)
+        sigma_sched = sig[steps - t_enc - 1:]
+        xi = init_latent + noise * sigma_sched[0]
+        if latent_mask is None:
+            return self._run_sampler(p, xi, sigma_sched, rng, cond, uncond, y_cond, y_uncond), init_latent
+        nmask = torch.round(latent_mask.to(self.device, torch.float32)).expand(init_latent.shape)
+        mask = 1.0 - nmask
+        cfg = CFGDenoiser(self.model_wrap)
+        cfg.init_latent, cfg.mask, cfg.nmask = init_latent, mask, nmask
+        extra = {"cond": cond, "uncond": uncond, "cond_scale": p.cfg_scale, "y_cond": y_cond, "y_uncond": y_uncond}
+        if p.sampler == "Euler a":
+            out = K.sample_euler_ancestral(cfg, xi, sigma_sched.to(xi.device), extra_args=extra, eta=p.eta, s_noise=p.s_noise,
+                                           noise_sampler=rng.next)
+        else:
+            out = K.sample_dpmpp_2m(cfg, xi, sigma_sched.to(xi.device), extra_args=extra)
+        return out * nmask + init_latent * mask, init_latent
+
     # -- decode --------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def decode(self, latents, scale_factor):

@@ -191,3 +191,30 @@ class AutoencoderKLDecode(nn.Module):
         return self.decoder(self.post_quant_conv(z))
 
     forward = decode
+
+
+class AutoencoderKLEncode(nn.Module):
+    """The other half of `first_stage_model`: encoder + quant_conv -> moments (mean | logvar); ldm AutoencoderKL.encode
+    returns DiagonalGaussianDistribution(moments). SURVEY §8(f) N1 (img2img init, modules/sd_samplers_common.py:87-112)."""
+
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = Encoder(cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg.z_channels, 2 * cfg.embed_dim, 1)
+
+    def encode_moments(self, x):
+        return self.quant_conv(self.encoder(x))
+
+    forward = encode_moments
+
+
+def gaussian_sample(moments, noise=None):
+    """ldm DiagonalGaussianDistribution: logvar clamped to [-30, 20]; sample = mean + std * noise; mode = mean."""
+    import torch
+
+    mean, logvar = torch.chunk(moments.float(), 2, dim=1)
+    if noise is None:
+        return mean
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise.float()
+

@@ -146,6 +146,30 @@ def vae_decoder_param_shapes(spec: VAESpec, embed_dim: int = 4) -> "OrderedDict[
     return d
 
 
+def vae_encoder_param_shapes(spec: VAESpec, embed_dim: int = 4) -> "OrderedDict[str, Tuple[int, ...]]":
+    """ldm Encoder + quant_conv (the other half of `first_stage_model`), state-dict order."""
+    d: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    _conv(d, "encoder.conv_in", spec.ch, spec.out_ch, 3)
+    bi = spec.ch
+    nl = len(spec.ch_mult)
+    for level in range(nl):
+        bo = spec.ch * spec.ch_mult[level]
+        for j in range(spec.num_res_blocks):
+            _vres(d, f"encoder.down.{level}.block.{j}", bi, bo)
+            bi = bo
+        if level != nl - 1:
+            _conv(d, f"encoder.down.{level}.downsample.conv", bi, bi, 3)
+    _vres(d, "encoder.mid.block_1", bi, bi)
+    _norm(d, "encoder.mid.attn_1.norm", bi)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(d, f"encoder.mid.attn_1.{n}", bi, bi, 1)
+    _vres(d, "encoder.mid.block_2", bi, bi)
+    _norm(d, "encoder.norm_out", bi)
+    _conv(d, "encoder.conv_out", 2 * spec.z_channels, bi, 3)
+    _conv(d, "quant_conv", 2 * embed_dim, 2 * spec.z_channels, 1)
+    return d
+
+
 def param_count(shapes) -> int:
     return sum(math.prod(s) for s in shapes.values())
 

@@ -146,6 +146,12 @@ struct sdxe_engine {
   VaeResW v_mid1, v_mid2;
   NormW v_attn_norm, v_norm_out;
   std::vector<std::vector<VaeResW>> v_up_blocks;  // [level][block], level index as in the state dict
+  // VAE encoder (ldm Encoder: conv_in, down.{l}.block.{j} (+ downsample), mid, norm_out, conv_out; then quant_conv)
+  LinW e_conv_in, e_conv_out, e_qkv, e_proj, e_quant;
+  VaeResW e_mid1, e_mid2;
+  NormW e_attn_norm, e_norm_out;
+  std::vector<std::vector<VaeResW>> e_down_blocks;
+  std::vector<LinW> e_down_conv;
   std::vector<LinW> v_up_conv;                    // per level (level 0 unused)
 
   // activation pool
@@ -170,6 +176,7 @@ struct sdxe_engine {
   int pack_f32(float*& out, const std::string& key, int64_t n);
   int build_unet();
   int build_vae();
+  int build_vae_encoder();
   int build_res(ResW& r, const std::string& p, int cin, int cout);
   int build_st(STW& s, const std::string& p, int C, int depth);
   int build_vae_res(VaeResW& r, const std::string& p, int cin, int cout);
@@ -856,6 +863,37 @@ int sdxe_engine::build_vae() {
   return 0;
 }
 
+int sdxe_engine::build_vae_encoder() {
+  const int z = cfg.vae_z_channels, nl = cfg.num_levels, nrb = cfg.num_res_blocks, ch = cfg.vae_ch, cin = cfg.vae_out_ch;
+  ECHK(pack_linear(e_conv_in, {"encoder.conv_in.weight"}, {"encoder.conv_in.bias"}, ch, 9 * cin, PACK_CONV3, conv_kpad(cin)));
+  e_down_blocks.assign(nl, {});
+  e_down_conv.assign(nl, LinW());
+  int bi = ch;
+  for (int level = 0; level < nl; ++level) {
+    const int bo = ch * cfg.channel_mult[level];
+    for (int j = 0; j < nrb; ++j) {
+      VaeResW r;
+      ECHK(build_vae_res(r, "encoder.down." + std::to_string(level) + ".block." + std::to_string(j), bi, bo));
+      e_down_blocks[level].push_back(r);
+      bi = bo;
+    }
+    if (level != nl - 1) {
+      const std::string d = "encoder.down." + std::to_string(level) + ".downsample.conv";
+      ECHK(pack_linear(e_down_conv[level], {d + ".weight"}, {d + ".bias"}, bi, 9 * bi, PACK_CONV3, conv_kpad(bi)));
+    }
+  }
+  ECHK(build_vae_res(e_mid1, "encoder.mid.block_1", bi, bi));
+  ECHK(pack_norm(e_attn_norm, "encoder.mid.attn_1.norm", bi));
+  ECHK(pack_linear(e_qkv, {"encoder.mid.attn_1.q.weight", "encoder.mid.attn_1.k.weight", "encoder.mid.attn_1.v.weight"},
+                   {"encoder.mid.attn_1.q.bias", "encoder.mid.attn_1.k.bias", "encoder.mid.attn_1.v.bias"}, bi, bi, PACK_PLAIN));
+  ECHK(pack_linear(e_proj, {"encoder.mid.attn_1.proj_out.weight"}, {"encoder.mid.attn_1.proj_out.bias"}, bi, bi, PACK_PLAIN));
+  ECHK(build_vae_res(e_mid2, "encoder.mid.block_2", bi, bi));
+  ECHK(pack_norm(e_norm_out, "encoder.norm_out", bi));
+  ECHK(pack_linear(e_conv_out, {"encoder.conv_out.weight"}, {"encoder.conv_out.bias"}, 2 * z, 9 * bi, PACK_CONV3, conv_kpad(bi)));
+  ECHK(pack_linear(e_quant, {"quant_conv.weight"}, {"quant_conv.bias"}, 2 * z, 2 * z, PACK_PLAIN));
+  return 0;
+}
+
 // =================================================================================================================
 // engine: activation pool
 // =================================================================================================================
@@ -1112,6 +1150,91 @@ __global__ void post_quant_kernel(const void* __restrict__ z, int io_dtype, cons
   }
 }
 
+// AttnBlock (sd_hijack_optimizations.py:637-655): GN -> fused q|k|v 1x1 conv -> single-head attention -> proj + x
+int vae_attn_block(sdxe_engine* e, Builder& B, Act& cur, const NormW& norm, const LinW& qkv_w, const LinW& proj_w) {
+  const int C = cur.c, tokens = cur.h * cur.w, n = cur.n;
+  const int64_t M = cur.rows();
+  Act xn;
+  ECHK(B.group_norm(cur, nullptr, norm, 1e-6f, false, xn));
+  Buf qkv = e->alloc((size_t)M * 3 * C * 2);
+  ECHK(B.gemm(xn.p, C, M, qkv_w, qkv.p, Builder::GemmOpt()));
+  B.free_act(xn);
+  if (C % 64 != 0 || C > 512) EFAIL("vae attention: channel count must be a multiple of 64 and <= 512");
+  Act att = B.new_act(n, cur.h, cur.w, C);
+  const uint16_t* qp = (const uint16_t*)qkv.p;
+  ECHK(B.attention(qp, qp + C, qp + 2 * C, n, 1, tokens, tokens, C, 3 * C, 3 * C, 1.0f / sqrtf((float)C), att.p, C, C));
+  e->release(qkv);
+  Act o = B.new_act(n, cur.h, cur.w, C);
+  Builder::GemmOpt op;
+  op.residual = cur.p; op.ldr = C;
+  ECHK(B.gemm(att.p, C, M, proj_w, o.p, op));
+  B.free_act(att);
+  B.free_act(cur);
+  cur = o;
+  return 0;
+}
+
+// AutoencoderKL.encode up to the moments: x [n, 3, H, W] -> [n, 2z, H/8, W/8]
+int build_vae_encode_plan(sdxe_engine* e, Plan* p, int n, int H, int W) {
+  const sdxe_config& cfg = e->cfg;
+  Builder B(e, p);
+  const bool bf16 = e->bf16;
+  const int nl = cfg.num_levels, cin = cfg.vae_out_ch, z2 = 2 * cfg.vae_z_channels;
+  const int64_t M0 = (int64_t)n * H * W;
+  const int kin = e->e_conv_in.ld;
+  Buf col0 = e->alloc((size_t)M0 * kin * 2);
+  {
+    void* c0 = col0.p;
+    p->pre.push_back([=](cudaStream_t s) { return im2col3x3_nchw_launch(p->x, p->io_dtype, c0, n, cin, H, W, kin, bf16, s); });
+  }
+  Act cur = B.new_act(n, H, W, cfg.vae_ch);
+  {
+    LinW Wc = e->e_conv_in;
+    Wc.K = Wc.ld;
+    ECHK(B.gemm(col0.p, Wc.ld, M0, Wc, cur.p, Builder::GemmOpt()));
+  }
+  Act t;
+  for (int level = 0; level < nl; ++level) {
+    for (const VaeResW& r : e->e_down_blocks[level]) {
+      ECHK(B.vae_res(r, cur, t));
+      B.free_act(cur);
+      cur = t;
+    }
+    if (level != nl - 1) {
+      // ldm Downsample (with_conv): pad (0,1,0,1) then conv3x3 stride 2, padding 0 -> taps start at the pixel itself
+      const int Ho = cur.h / 2, Wo = cur.w / 2;
+      Act d = B.new_act(n, Ho, Wo, cur.c);
+      ECHK(B.conv3_im2col(cur, e->e_down_conv[level], d.p, cur.c, Builder::GemmOpt(), 2, 0, Ho, Wo));
+      B.free_act(cur);
+      cur = d;
+    }
+  }
+  ECHK(B.vae_res(e->e_mid1, cur, t));
+  B.free_act(cur);
+  cur = t;
+  ECHK(vae_attn_block(e, B, cur, e->e_attn_norm, e->e_qkv, e->e_proj));
+  ECHK(B.vae_res(e->e_mid2, cur, t));
+  B.free_act(cur);
+  cur = t;
+  Act g;
+  ECHK(B.group_norm(cur, nullptr, e->e_norm_out, 1e-6f, true, g));
+  const int Ho = cur.h, Wo = cur.w;
+  B.free_act(cur);
+  const int ld8 = (int)align_up(z2, 8);
+  Act mo = B.new_act(n, Ho, Wo, ld8);
+  ECHK(B.conv3(g, e->e_conv_out, mo.p, ld8, Builder::GemmOpt()));
+  B.free_act(g);
+  Buf outb = e->alloc((size_t)n * Ho * Wo * ld8 * 2);
+  ECHK(B.gemm(mo.p, ld8, (int64_t)n * Ho * Wo, e->e_quant, outb.p, Builder::GemmOpt()));  // quant_conv (1x1)
+  B.free_act(mo);
+  {
+    void* ob = outb.p;
+    const int hw = Ho * Wo;
+    p->post.push_back([=](cudaStream_t s) { return nhwc_to_nchw_launch(ob, ld8, p->out, p->io_dtype, n, z2, hw, bf16, s); });
+  }
+  return 0;
+}
+
 int build_vae_plan(sdxe_engine* e, Plan* p, int n, int h, int w) {
   const sdxe_config& cfg = e->cfg;
   Builder B(e, p);
@@ -1148,28 +1271,7 @@ int build_vae_plan(sdxe_engine* e, Plan* p, int n, int h, int w) {
   ECHK(B.vae_res(e->v_mid1, cur, t));
   B.free_act(cur);
   cur = t;
-  {
-    // AttnBlock (sd_hijack_optimizations.py:637-655): GN -> fused q|k|v 1x1 conv -> single-head attention -> proj + x
-    const int C = cur.c, tokens = cur.h * cur.w;
-    Act xn;
-    ECHK(B.group_norm(cur, nullptr, e->v_attn_norm, 1e-6f, false, xn));
-    Buf qkv = e->alloc((size_t)M0 * 3 * C * 2);
-    ECHK(B.gemm(xn.p, C, M0, e->v_qkv, qkv.p, Builder::GemmOpt()));
-    B.free_act(xn);
-    const int dpad = (C + 63) / 64 * 64;
-    if (dpad != C || C > 512) EFAIL("vae attention: channel count must be a multiple of 64 and <= 512");
-    Act att = B.new_act(n, cur.h, cur.w, C);
-    const uint16_t* qp = (const uint16_t*)qkv.p;
-    ECHK(B.attention(qp, qp + C, qp + 2 * C, n, 1, tokens, tokens, C, 3 * C, 3 * C, 1.0f / sqrtf((float)C), att.p, C, C));
-    e->release(qkv);
-    Act o = B.new_act(n, cur.h, cur.w, C);
-    Builder::GemmOpt op;
-    op.residual = cur.p; op.ldr = C;
-    ECHK(B.gemm(att.p, C, M0, e->v_proj, o.p, op));
-    B.free_act(att);
-    B.free_act(cur);
-    cur = o;
-  }
+  ECHK(vae_attn_block(e, B, cur, e->v_attn_norm, e->v_qkv, e->v_proj));
   ECHK(B.vae_res(e->v_mid2, cur, t));
   B.free_act(cur);
   cur = t;
@@ -1223,7 +1325,7 @@ int sdxe_create(const sdxe_config* cfg, sdxe_engine** out) {
   if (cfg->kind == SDXE_MODEL_UNET) {
     if (cfg->model_channels % 32) EFAIL("sdxe_create: model_channels must be a multiple of 32");
     if (cfg->context_dim % 8) EFAIL("sdxe_create: context_dim % 8");
-  } else if (cfg->kind == SDXE_MODEL_VAE_DECODER) {
+  } else if (cfg->kind == SDXE_MODEL_VAE_DECODER || cfg->kind == SDXE_MODEL_VAE_ENCODER) {
     if (cfg->vae_ch % 32) EFAIL("sdxe_create: vae_ch must be a multiple of 32");
   } else {
     EFAIL("sdxe_create: unknown model kind");
@@ -1275,7 +1377,7 @@ int sdxe_finalize(sdxe_engine* e) {
     e->sizing = pass == 0;
     e->cursor = 0;
     e->missing.clear();
-    int rc = e->cfg.kind == SDXE_MODEL_UNET ? e->build_unet() : e->build_vae();
+    int rc = e->cfg.kind == SDXE_MODEL_UNET ? e->build_unet() : (e->cfg.kind == SDXE_MODEL_VAE_ENCODER ? e->build_vae_encoder() : e->build_vae());
     if (rc != 0) return -1;
     if (!e->missing.empty()) {
       std::string m = "sdxe_finalize: missing / mis-shaped weights: " + e->missing;
@@ -1351,6 +1453,24 @@ int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int 
   }
   Plan* p = it->second.get();
   p->x = z; p->out = out; p->io_dtype = io_dtype;
+  return run_plan(e, p, (cudaStream_t)stream);
+}
+
+int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int w, int io_dtype, void* stream) {
+  if (!e || !e->finalized || e->cfg.kind != SDXE_MODEL_VAE_ENCODER) EFAIL("sdxe_vae_encode: engine is not a finalized VAE encoder");
+  const int f = 1 << (e->cfg.num_levels - 1);  // spatial reduction of the encoder (8 for the SD VAE)
+  if (!x || !out || n <= 0 || h <= 0 || w <= 0 || (h % f) || (w % f)) EFAIL("sdxe_vae_encode: bad argument (H, W must be multiples of the encoder's downsampling factor)");
+  if (io_dtype != SDXE_F16 && io_dtype != SDXE_BF16 && io_dtype != SDXE_F32) EFAIL("sdxe_vae_encode: io dtype");
+  const std::string key = "e:" + std::to_string(n) + ":" + std::to_string(h) + ":" + std::to_string(w);
+  auto it = e->plans.find(key);
+  if (it == e->plans.end()) {
+    std::unique_ptr<Plan> p(new Plan());
+    p->e = e;
+    if (build_vae_encode_plan(e, p.get(), n, h, w) != 0) return -1;
+    it = e->plans.emplace(key, std::move(p)).first;
+  }
+  Plan* p = it->second.get();
+  p->x = x; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
 }
 

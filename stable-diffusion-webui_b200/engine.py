@@ -229,3 +229,48 @@ class VAEDecoderEngine(_EngineBase):
         return out
 
     __call__ = decode
+
+
+class VAEEncoderEngine(_EngineBase):
+    """AutoencoderKL.encode up to the moments (encoder + quant_conv): the img2img / hires non-latent entry
+    (modules/sd_samplers_common.py:87-112 images_tensor_to_samples -> model.encode_first_stage)."""
+
+    def __init__(self, spec: VAESpec, dtype: torch.dtype = torch.float16, device="cuda:0"):
+        cfg = L.SdxeConfig()
+        cfg.kind = L.SDXE_MODEL_VAE_ENCODER
+        cfg.dtype = _dtype_code(dtype)
+        cfg.num_levels = len(spec.ch_mult)
+        for i, m in enumerate(spec.ch_mult):
+            cfg.channel_mult[i] = m
+        cfg.num_res_blocks = spec.num_res_blocks
+        cfg.vae_ch, cfg.vae_z_channels, cfg.vae_out_ch = spec.ch, spec.z_channels, spec.out_ch
+        self.spec = spec
+        super().__init__(cfg, dtype, device)
+
+    def load_state_dict(self, sd, prefix: str = "", only=("encoder.", "quant_conv.")):
+        return super().load_state_dict(sd, prefix, only)
+
+    def encode_moments(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [n,3,H,W] in [-1,1] -> moments [n, 2*z, H/f, W/f] (mean | logvar), same dtype as x."""
+        if not x.is_cuda:
+            raise L.SdxeError("sdxe VAE needs CUDA tensors: there is no CPU fallback")
+        x = x.contiguous()
+        n, _, h, w = x.shape
+        f = 2 ** (len(self.spec.ch_mult) - 1)
+        if out is None:
+            out = torch.empty(n, 2 * self.spec.z_channels, h // f, w // f, dtype=x.dtype, device=x.device)
+        L.check(self.lib.sdxe_vae_encode(self._h, L.ptr(x), L.ptr(out), n, h, w, L.torch_dtype_code(x.dtype),
+                                         L.current_stream()), "sdxe_vae_encode")
+        return out
+
+    def encode(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """DiagonalGaussianDistribution(moments).sample() (ldm distributions.py: logvar clamped to [-30, 20],
+        mean + exp(0.5 logvar) * noise); noise=None returns the mode (the mean), as `sd_vae_encode_method` "Mode"."""
+        m = self.encode_moments(x).float()
+        mean, logvar = torch.chunk(m, 2, dim=1)
+        if noise is None:
+            return mean
+        return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise.float()
+
+    __call__ = encode_moments
+

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdxe.so")
 
 SDXE_F16, SDXE_BF16, SDXE_F32 = 0, 1, 2
-SDXE_MODEL_UNET, SDXE_MODEL_VAE_DECODER = 0, 1
+SDXE_MODEL_UNET, SDXE_MODEL_VAE_DECODER, SDXE_MODEL_VAE_ENCODER = 0, 1, 2
 SDXE_MAX_LEVELS = 8
 
 
@@ -59,6 +59,7 @@ SYMBOLS = {
     "sdxe_weight_blob": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
     "sdxe_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdxe_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdxe_vae_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdxe_profile": (c_int, [c_void_p, c_int]),
     "sdxe_profile_read": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "sdxe_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),

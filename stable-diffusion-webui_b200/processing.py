@@ -30,9 +30,10 @@ class SdModel:
     """What the hot path needs of `shared.sd_model`: the (replacement) UNet, the VAE decoder, the noise schedule."""
 
     def __init__(self, unet: SdxeUnet, vae: Optional[VAEDecoderEngine], is_sdxl: bool, dtype_unet=torch.float16,
-                 device="cuda:0", scale_factor: Optional[float] = None):
+                 device="cuda:0", scale_factor: Optional[float] = None, vae_encoder=None):
         self.unet = unet
         self.vae = vae
+        self.vae_encoder = vae_encoder  # engine.VAEEncoderEngine, only needed by img2img
         self.is_sdxl = is_sdxl
         self.dtype_unet = dtype_unet
         self.dtype_vae = dtype_unet
@@ -60,6 +61,29 @@ class SdModel:
         if self.vae is None:
             raise L.SdxeError("no VAE decoder engine attached")
         return self.vae.decode((z.to(self.dtype_vae) / self.scale_factor).contiguous())
+
+
+    # ldm LatentDiffusion.encode_first_stage / get_first_stage_encoding: moments -> scale_factor * sample
+    def encode_first_stage(self, x):
+        if self.vae_encoder is None:
+            raise L.SdxeError("no VAE encoder engine attached (img2img needs one)")
+        return self.vae_encoder.encode_moments(x.to(self.dtype_vae).contiguous())
+
+    def get_first_stage_encoding(self, moments, noise=None):
+        m = moments.float()
+        mean, logvar = torch.chunk(m, 2, dim=1)
+        if noise is None:  # reference: DiagonalGaussianDistribution.sample() draws from the GLOBAL torch RNG
+            noise = torch.randn(mean.shape, device=mean.device, dtype=torch.float32)
+        z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise.float()
+        return self.scale_factor * z
+
+
+def images_tensor_to_samples(image: torch.Tensor, model: SdModel, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """modules/sd_samplers_common.py:87-112 ("Full" VAE encode method): image [B,3,H,W] in [0,1] -> latent [B,4,H/8,W/8].
+    The reference encodes image by image; the engine takes the batch (per-sample norms / attention: same result).
+    `noise` pins the posterior sample (the reference's comes from the global RNG — SURVEY N1 calls this a parity hazard)."""
+    x = image.to(model.device, dtype=model.dtype_vae) * 2 - 1
+    return model.get_first_stage_encoding(model.encode_first_stage(x), noise)
 
 
 @dataclass
@@ -110,6 +134,52 @@ class StableDiffusionProcessingTxt2Img:
         noise = self.rng.next()
         self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
         return self.sampler.sample_img2img(self, samples, noise, self.c, self.uc, steps=self.hr_second_pass_steps or self.steps)
+
+
+@dataclass
+class StableDiffusionProcessingImg2Img(StableDiffusionProcessingTxt2Img):
+    """modules/processing.py:1527-1790 restricted to the latent path: init image -> VAE encode -> noise at
+    denoising_strength -> sampler.sample_img2img -> (optional latent mask blend). Resize modes, PIL mask
+    pre-processing, inpainting-model conditioning and colour correction stay upstream of the path."""
+    init_images: torch.Tensor = None     # [B,3,H,W] float in [0,1]
+    latent_mask: torch.Tensor = None     # [B or 1, 1 or 4, H/8, W/8] float, 1 = repaint (the reference's `nmask`)
+    mask_round: bool = True
+    inpainting_fill: int = 1             # 1 original (0 "fill" needs the pixel-space blur), 2 latent noise, 3 latent nothing
+    encode_noise: torch.Tensor = None    # pins the VAE posterior sample (None: torch.randn, as the reference)
+    init_latent: torch.Tensor = None
+    mask: torch.Tensor = None
+    nmask: torch.Tensor = None
+
+    def init(self, seeds):
+        if self.init_images is None:
+            raise L.SdxeError("img2img without init_images")
+        img = self.init_images
+        if img.shape[-2] != self.height or img.shape[-1] != self.width:
+            raise L.SdxeError("init_images must already have the target height x width (resize modes are upstream)")
+        if img.shape[0] == 1 and self.batch_size > 1:
+            img = img.expand(self.batch_size, -1, -1, -1)
+        self.init_latent = images_tensor_to_samples(img, self.sd_model, self.encode_noise)
+        if self.latent_mask is not None:
+            lat = self.latent_mask.to(self.init_latent.device, torch.float32)
+            if self.mask_round:
+                lat = torch.round(lat)
+            lat = lat.expand(self.init_latent.shape)
+            self.mask, self.nmask = 1.0 - lat, lat                                  # processing.py:1742-1743
+            if self.inpainting_fill == 2:                                           # :1746-1748
+                rnd = ImageRNG(tuple(self.init_latent.shape[1:]), seeds, source=self.randn_source, device=self.sd_model.device).next()
+                self.init_latent = self.init_latent * self.mask + rnd * self.nmask
+            elif self.inpainting_fill == 3:                                         # :1750-1752
+                self.init_latent = self.init_latent * self.mask
+
+    # modules/processing.py:1759-1779
+    def sample(self, conditioning, unconditional_conditioning, seeds):
+        self.init(seeds)
+        x = self.rng.next()
+        self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
+        samples = self.sampler.sample_img2img(self, self.init_latent, x, conditioning, unconditional_conditioning)
+        if self.mask is not None:
+            samples = samples * self.nmask + self.init_latent * self.mask
+        return samples
 
 
 @dataclass

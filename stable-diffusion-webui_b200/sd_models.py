@@ -183,8 +183,15 @@ def vae_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
             if k.startswith(VAE_PREFIX + "decoder.") or k.startswith(VAE_PREFIX + "post_quant_conv.")}
 
 
-def load_model(checkpoint_file: str, dtype=torch.float16, device="cuda:0", vae_file: Optional[str] = None):
-    """Checkpoint file -> a ready `processing.SdModel` (UNet engine activated, VAE decoder finalized).
+def vae_encoder_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    return {k[len(VAE_PREFIX):]: _compute_ready(v) for k, v in sd.items()
+            if k.startswith(VAE_PREFIX + "encoder.") or k.startswith(VAE_PREFIX + "quant_conv.")}
+
+
+def load_model(checkpoint_file: str, dtype=torch.float16, device="cuda:0", vae_file: Optional[str] = None,
+               with_encoder: bool = False):
+    """Checkpoint file -> a ready `processing.SdModel` (UNet engine activated, VAE decoder finalized; with_encoder also
+    builds the VAE encoder engine img2img needs).
     `vae_file`: external VAE (`--vae-path` / sd_vae.py) whose keys are un-prefixed `decoder.*` / `post_quant_conv.*`."""
     from .processing import SdModel
     from .sd_unet import SdxeUnet
@@ -204,4 +211,15 @@ def load_model(checkpoint_file: str, dtype=torch.float16, device="cuda:0", vae_f
         vae = VAEDecoderEngine(info.vae, dtype=dtype, device=torch.device(device))
         vae.load_state_dict(vsd)
         vae.finalize()
-    return SdModel(unet, vae, is_sdxl=info.kind == "sdxl", dtype_unet=dtype, device=device), info
+    enc = None
+    if with_encoder:
+        from .engine import VAEEncoderEngine
+
+        esd = ({k: _compute_ready(v) for k, v in ext.items() if k.startswith(("encoder.", "quant_conv."))} if vae_file
+               else vae_encoder_state_dict(sd))
+        if not esd:
+            raise L.SdxeError("with_encoder: the checkpoint has no first_stage_model.encoder.* tensors")
+        enc = VAEEncoderEngine(info.vae, dtype=dtype, device=torch.device(device))
+        enc.load_state_dict(esd)
+        enc.finalize()
+    return SdModel(unet, vae, is_sdxl=info.kind == "sdxl", dtype_unet=dtype, device=device, vae_encoder=enc), info

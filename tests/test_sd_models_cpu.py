@@ -116,3 +116,21 @@ def test_prefix_split_and_fp8_upcast():
     assert set(v) == {"decoder.conv_in.bias"} and u["out.2.bias"].dtype == torch.float32
     if "w8" in u:
         assert u["w8"].dtype == torch.float16 and torch.equal(u["w8"].float(), sd[M.UNET_PREFIX + "w8"].float())
+
+
+def test_vae_encoder_layout_matches_the_oracle():
+    """N1: the engine's expected encoder keys / shapes are exactly the oracle module's (ldm Encoder + quant_conv)."""
+    from oracle.vae import AutoencoderKLEncode, VAEConfig, gaussian_sample, tiny_vae_config
+    from sdwebui_b200 import checkpoint as C
+    from sdwebui_b200.engine import VAESpec
+
+    for cfg in (VAEConfig(), tiny_vae_config()):
+        m = AutoencoderKLEncode(cfg)
+        shapes = C.vae_encoder_param_shapes(VAESpec.from_any(cfg), cfg.embed_dim)
+        sd = m.state_dict()
+        assert list(shapes) == list(sd) and all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
+    assert C.param_count(C.vae_encoder_param_shapes(VAESpec())) == 34163592 + 72
+    mom = torch.cat([torch.full((1, 4, 2, 2), 0.5), torch.full((1, 4, 2, 2), 40.0)], 1)  # logvar above the clamp
+    assert torch.equal(gaussian_sample(mom), torch.full((1, 4, 2, 2), 0.5))
+    s = gaussian_sample(mom, torch.ones(1, 4, 2, 2))
+    assert torch.allclose(s, torch.full((1, 4, 2, 2), 0.5 + float(torch.exp(torch.tensor(10.0)))))
