@@ -51,10 +51,14 @@ class SdxeUnet(_SdUnetBase):
     """SdUnet whose forward is `sdxe_unet_forward`. Owns its weights (modules/sd_unet.py:54 moves the stock UNet away)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], spec: Optional[UNetSpec] = None, dtype=torch.float16,
-                 device="cuda:0", prefix: str = ""):
+                 device="cuda:0", prefix: str = "", loras=None):
+        """`loras`: [(lora_state_dict, unet_multiplier), ...] merged into the weights at activate() — the reference
+        merges lazily inside the stock modules, which a weight-snapshotting SdUnet would never see."""
         super().__init__()
         self._sd = state_dict
         self._prefix = prefix
+        self.loras = list(loras or [])
+        self.lora_reports = []
         self.spec = spec
         self.dtype = dtype
         self.device_ = torch.device(device)
@@ -65,6 +69,10 @@ class SdxeUnet(_SdUnetBase):
             return
         sd = {k[len(self._prefix):]: v for k, v in self._sd.items() if k.startswith(self._prefix)}
         spec = self.spec or guess_unet_spec(sd)
+        if self.loras:
+            from .extra_networks_lora import merge_loras
+
+            sd, self.lora_reports = merge_loras(sd, self.loras)
         eng = UNetEngine(spec, dtype=self.dtype, device=self.device_)
         eng.load_state_dict(sd)
         eng.finalize()
