@@ -31,5 +31,9 @@ int attention2_init();
 bool attentionx_eligible(const AttnArgs& a);
 int attentionx_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
 int attentionx_init();
+// two Q tiles, one softmax thread per query row, S handed back to the MMA warp right after the register copy (attention4.cu)
+bool attention4_eligible(const AttnArgs& a);
+int attention4_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
+int attention4_init();
 
 }  // namespace sdxe
