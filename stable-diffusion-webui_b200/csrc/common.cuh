@@ -134,6 +134,7 @@ SDXE_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1
 }
 SDXE_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 SDXE_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
+SDXE_DEVINL void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }    // all but the newest group
 SDXE_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }            // writes done
 
 // multicast variant: the box lands at the same smem offset in every CTA of `mask`, each CTA's mbarrier (same offset)

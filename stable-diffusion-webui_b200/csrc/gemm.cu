@@ -32,7 +32,7 @@ static constexpr int TMEM_COLS = 512;
 static constexpr int SBIAS_BYTES = 4 * 256 * 4;  // per-tile bias and LayerNorm-fold c1 slices in smem, double buffered
 static constexpr int CHUNK_BYTES = 32 * 32 * 2;   // one epilogue chunk: 32 rows x 32 columns, 16 bit
 static constexpr int NUM_EPI_WARPS = 8;
-static constexpr int NUM_BARS_FIXED = 4 + 2 * NUM_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][2]
+static constexpr int NUM_BARS_FIXED = 4 + 3 * NUM_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][<= 3 buffers]
 
 // EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
@@ -54,11 +54,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * S + 4 + 2 * w + b); };
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * S + 4 + 3 * w + b); };
   const uint32_t misc_off = S * stage_bytes + 8 * (2 * S + NUM_BARS_FIXED);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + misc_off);
   float* sbias = reinterpret_cast<float*>(smem + misc_off + 16);  // [2][256]
-  constexpr int NBUF = RES ? 2 : 1;  // staging chunks per epilogue warp (residual in flight needs the second one)
+  // staging chunks per epilogue warp: one more than strictly needed (plain 2, residual 3) lets chunk c be written while
+  // the TMA store of chunk c-1 is still reading its buffer (the store's smem read latency otherwise serialises the
+  // chunks: measured ~5.5 k cycles per 128 x 160 tile of pure epilogue); falls back to 1 / 2 when smem is short
+  const int NBUF = a.epi_bufs;
+  const bool deep = NBUF > (RES ? 2 : 1);
   const uint32_t stage_buf_base = (smem_base + misc_off + 16 + SBIAS_BYTES + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       mbar_init(tempty_bar(i), clustered ? 16 : 8);  // paired: both CTAs' epilogue warps free the leader's accumulator
     }
     if (RES)
-      for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); mbar_init(res_bar(w, 2), 1); }
     fence_mbar_init();
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
@@ -264,15 +268,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         ln_rs = rsqrtf(fmaxf(pq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
       }
       float st_s = 0.f, st_q = 0.f;  // STAT: this thread's share of its row's (sum, sum of squares)
-      auto res_load = [&](int c0, uint32_t ctr) {  // elected lane: residual chunk -> staging buffer ctr & 1
-        const uint32_t b = ctr & 1u;
+      auto res_load = [&](int c0, uint32_t ctr) {  // elected lane: residual chunk -> staging buffer ctr % NBUF
+        const uint32_t b = ctr % (uint32_t)NBUF;
         const int nc = min(32, out_cols - c0);
         mbar_expect_tx(res_bar(ew, b), (uint32_t)nc * 64u);
         tma_load_2d(my_buf + b * CHUNK_BYTES, nc == 32 ? &a.tmR : &a.tmR16, res_bar(ew, b), n_out0 + c0, row0);
       };
       if (RES && ehalf * 32 < out_cols) {  // (a tile narrower than 33 columns leaves the second warp of a quarter idle)
         // first chunk's residual travels while the accumulator is still being produced
-        if (elect_one()) { bulk_wait_read_all(); res_load(ehalf * 32, chunk_ctr); }
+        if (elect_one()) {
+          if (deep) bulk_wait_read_1(); else bulk_wait_read_all();
+          res_load(ehalf * 32, chunk_ctr);
+        }
         __syncwarp();
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all epilogue warps
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
       for (int c0 = ehalf * 32; c0 < out_cols; c0 += 64, ++chunk_ctr) {
         const int nc = min(32, out_cols - c0);
-        const uint32_t b = RES ? (chunk_ctr & 1u) : 0u;
+        const uint32_t b = chunk_ctr % (uint32_t)NBUF;
         const uint32_t buf = my_buf + b * CHUNK_BYTES;
         uint32_t r[32];
         uint32_t rg[GEGLU ? 32 : 1];
@@ -298,11 +305,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         if (RES) {
           // the other buffer is free once the previous chunk's store has read it: fetch the next residual chunk into it
           if (elect_one()) {
-            bulk_wait_read_all();
+            if (deep) bulk_wait_read_1(); else bulk_wait_read_all();  // the next chunk's buffer was read by store(c-2) / store(c-1)
             if (c0 + 64 < out_cols) res_load(c0 + 64, chunk_ctr + 1);
           }
           __syncwarp();
-          mbar_wait(res_bar(ew, b), (chunk_ctr >> 1) & 1u);
+          mbar_wait(res_bar(ew, b), (chunk_ctr / (uint32_t)NBUF) & 1u);
         }
         tc_wait_ld();
         // this thread's row piece inside the chunk: 16-byte unit g at (lane * rowbytes + 16 g) ^ swizzle
@@ -386,8 +393,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           }
         }
         if (!RES) {
-          // single staging buffer: the previous chunk's store must have read it before it is overwritten
-          if (elect_one()) bulk_wait_read_all();
+          // this buffer was last read by the store of chunk c - NBUF: it must be done before the buffer is overwritten
+          if (elect_one()) { if (deep) bulk_wait_read_1(); else bulk_wait_read_all(); }
           __syncwarp();
         }
 #pragma unroll
@@ -450,19 +457,26 @@ bool conv_tile_shape(int H, int W, int* bw, int* bh, int* bn) {
   return true;
 }
 
-static size_t gemm_smem_fixed(int num_stages, bool residual) {  // everything but the operand stages
+static size_t gemm_smem_fixed(int num_stages, int epi_bufs) {  // everything but the operand stages
   return 1024 /*base alignment*/ + 8 * (2 * num_stages + NUM_BARS_FIXED) + 16 + SBIAS_BYTES + 1024 /*staging alignment*/ +
-         (size_t)NUM_EPI_WARPS * (residual ? 2 : 1) * CHUNK_BYTES;
+         (size_t)NUM_EPI_WARPS * epi_bufs * CHUNK_BYTES;
 }
-int gemm_pick_stages(int BN, bool residual) {
+int gemm_pick_stages(int BN, int epi_bufs) {
   const int stage_bytes = A_STAGE_BYTES + BN * 128;
-  int s = (int)((227 * 1024 - gemm_smem_fixed(8, residual)) / stage_bytes);
+  int s = (int)((227 * 1024 - gemm_smem_fixed(8, epi_bufs)) / stage_bytes);
   return std::max(2, std::min(s, 8));
 }
 int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld) {
   a.cluster = (a.c1 || a.stat_out) ? 1 : gemm_pick_cluster(a.M, a.BN);  // fold / statistics variants are un-paired only
   const int bn_cta = a.cluster == 2 ? a.BN / 2 : a.BN;
-  a.num_stages = gemm_pick_stages(bn_cta, a.residual != nullptr);
+  // one staging buffer more than the minimum unless that costs an operand stage below four
+  const int min_bufs = a.residual ? 2 : 1;
+  const int s_min = gemm_pick_stages(bn_cta, min_bufs), s_deep = gemm_pick_stages(bn_cta, min_bufs + 1);
+  static int deep_ok = -1;
+  // default off: measured no gain (same-box A/B, SD1.5 UNet 18.74 / 18.76 ms with vs 18.65 / 18.98 ms without)
+  if (deep_ok < 0) { const char* e = getenv("SDXE_EPI_DEEP"); deep_ok = e ? atoi(e) : 0; }
+  a.epi_bufs = (deep_ok && (s_deep == s_min || s_deep >= 4)) ? min_bufs + 1 : min_bufs;
+  a.num_stages = a.epi_bufs > min_bufs ? s_deep : s_min;
   if (make_tmap_2d(&a.tmB, W, w_rows, a.K, w_ld, bn_cta)) return -1;
   const int64_t out_cols = a.epi == EPI_GEGLU ? a.N / 2 : (a.N + 7) / 8 * 8;
   if (a.ldo % 8 || (a.residual && a.ldr % 8)) { set_last_error(__FILE__, __LINE__, "gemm: ldo / ldr must be multiples of 8"); return -1; }
@@ -541,7 +555,8 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
   const int stage_bytes = A_STAGE_BYTES + (a.cluster == 2 ? a.BN / 2 : a.BN) * 128;
-  const size_t smem = (size_t)a.num_stages * stage_bytes + gemm_smem_fixed(a.num_stages, a.residual != nullptr);
+  if (a.epi_bufs < (a.residual ? 2 : 1) || a.epi_bufs > 3) { set_last_error(__FILE__, __LINE__, "gemm: epi_bufs (call gemm_finish_args)"); return -1; }
+  const size_t smem = (size_t)a.num_stages * stage_bytes + gemm_smem_fixed(a.num_stages, a.epi_bufs);
   if (smem > 227 * 1024) { set_last_error(__FILE__, __LINE__, "gemm: shared memory budget"); return -1; }
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;
   const int tiles = num_m * num_n;

@@ -22,6 +22,7 @@ struct alignas(64) GemmArgs {
   int K1;            // K elements sourced from tmA (== K when there is no second segment)
   int BN;            // tile width (multiple of 16, <= 256)
   int num_stages;
+  int epi_bufs;      // staging chunks per epilogue warp (set by gemm_finish_args): plain 1-2, residual 2-3
   int conv;          // 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 NHWC implicit GEMM
   int cblocks;       // conv: Cin / 64
   int H, W;          // conv: image size; tile = bn images x bh rows x bw pixels (bw == W, or 128 | W)
@@ -52,7 +53,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream);
 int gemm_init();  // one-time kernel attribute setup (call before any stream capture)
 // Tile-width heuristic: pick BN for an [M, N] output (geglu needs BN % 32 == 0 and N % BN == 0).
 int gemm_pick_bn(int M, int N, int K, int epi);
-int gemm_pick_stages(int BN, bool residual);
+int gemm_pick_stages(int BN, int epi_bufs);
 int gemm_pick_cluster(int M, int BN);  // 2 when CTA pairs (cta_group::2) are enabled and the geometry allows, else 1
 // After M/N/K/K1/BN/epi/tmA/out/ldo/residual/ldr are set: picks cluster + stage count, builds tmB over the packed
 // weights W [w_rows, K] (row pitch w_ld) and the epilogue's store / residual maps.
