@@ -5,9 +5,11 @@
 namespace sdxe {
 
 struct alignas(64) AttnArgs {
-  CUtensorMap tmQ;  // 3D {dqk_pad, Nq, B*H}, box 64 x 128 x 1
-  CUtensorMap tmK;  // 3D {dqk_pad, Nk, B*H}
-  CUtensorMap tmV;  // 3D {dv_pad,  Nk, B*H}
+  // 4D per-head views (common.cuh make_tmap_heads): {d (true head dim: boxes reaching past it are zero-filled), token,
+  // head, batch}, box 64 x 128 x 1 x 1, 128B swizzle
+  CUtensorMap tmQ;
+  CUtensorMap tmK;
+  CUtensorMap tmV;
   int B, H, Nq, Nk;
   int dqk_slabs;    // dqk_pad / 64  (1..8)
   int dv_slabs;     // dv_pad / 64   (1..4)

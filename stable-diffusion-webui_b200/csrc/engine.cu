@@ -367,14 +367,6 @@ struct Builder {
     e->release(st);
     return 0;
   }
-  int layer_norm(const void* x, int64_t rows, const NormW& nw, void* out) {
-    const float *g = nw.g, *bt = nw.b;
-    const int C = nw.C;
-    const bool b = bf16;
-    ops->push_back(OpRec([=](cudaStream_t s) { return layer_norm_launch(x, g, bt, out, (int)rows, C, 1e-5f, b, s); }, K_LNORM, 0.0,
-                         4.0 * (double)rows * C, "ln rows=" + std::to_string(rows) + " C=" + std::to_string(C)));
-    return 0;
-  }
   // q: [B*Nq, ldq], k / v: [B*Nk, ldkv] row-major activations whose columns h*d .. h*d+d-1 belong to head h (the
   // projection GEMM's natural output). The kernels see them through 4D tensor maps (d, token, head, batch); a 64-wide
   // box reaching past d is zero-filled by TMA, so no padded per-head copy exists.

@@ -6,6 +6,9 @@
 //   * ResBlock / Upsample / VAE conv3x3      (ldm openaimodel.py ResBlock) -> conv mode
 //   * conv1x1 proj_in/proj_out/skip, Linear q/k/v/out/FF                          -> plain mode
 //   * GEGLU (ldm attention.py GEGLU: x * gelu(gate))                                         -> EPI_GEGLU
+//   * nn.LayerNorm in front of q/k/v, cross-attention q and the feed-forward (BasicTransformerBlock norm1-3)
+//     -> folded: the producing GEMM emits per-row (sum, sum of squares) (STAT), the consuming GEMM normalises in its
+//        epilogue (LNF) with gamma / beta pre-multiplied into its packed weight / bias (gemm.cuh)
 //
 // Structure (one CTA per SM, persistent over output tiles of 128 x BN):
 //   warp 0   : TMA producer. A tile = 128 rows x 64 K (16 KB, 128B swizzle). In conv mode the A tile is a
