@@ -104,6 +104,33 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # the reference arm / cpu_baseline: the oracle (= reference arithmetic) on the host cores, fp32, bounded sample
 # ----------------------------------------------------------------------------------------------------------------------
+def effective_cores() -> int:
+    """Host threads this process can really use: cpu_count capped by the affinity mask and the cgroup CPU quota
+    (asking torch for 128 threads inside a container that is throttled to a few cores makes the CPU arm ~10x slower
+    than it should be, which would flatter the GPU / CPU ratio)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                txt = f.read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                        n = min(n, max(1, int(q / int(g.read()) + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def cpu_reference_sample(config: str, budget_note=True) -> dict:
     """SD1.5: one CFG UNet call (2 x 64x64 samples = one Euler-a step of ONE image) + one 512x512 VAE decode, timed;
     images/s is extrapolated as 1 / (steps * t_step + t_decode) and labelled as such. SDXL: same at 128x128 / 1024."""
@@ -112,7 +139,7 @@ def cpu_reference_sample(config: str, budget_note=True) -> dict:
     from oracle.vae import AutoencoderKLDecode, VAEConfig
 
     w = WORKLOADS[config]
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     torch.set_num_threads(cores)
     cfg = sd15_config() if config == "sd15" else sdxl_config()
     h, wd = w["height"] // 8, w["width"] // 8
@@ -390,7 +417,7 @@ def main():
                 cb = cpu_reference_sample(args.config)
                 extras["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:  # noqa: BLE001
-                extras["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port", "sample": repr(ex)[:200]}
+                extras["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": effective_cores(), "kind": "port", "sample": repr(ex)[:200]}
         h2d = nbytes(c_host) + nbytes(u_host)
         d2h = B * w["height"] * w["width"] * 3
         line = {"metric": f"images/sec {w['name']}", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
