@@ -4,6 +4,8 @@
 
 philox_ref.npz   outputs of the REFERENCE's own modules/rng_philox.py (imported from /root/reference) for a few
                  (seed, shape, call-index) triples: pins oracle/rng.py and the product's rng.py bit-for-bit.
+prompt_attention.json  outputs of the REFERENCE's modules/prompt_parser.py parse_prompt_attention (module loaded from
+                 /root/reference) for hand-written and fuzzed prompts: pins sdwebui_b200/prompt_parser.py exactly.
 tiny_oracle.npz  outputs of the oracle itself on the tiny UNet / VAE / samplers with seeded weights (regression
                  fixture: guards the oracle against accidental edits; it is NOT an external ground truth).
 """
@@ -33,6 +35,36 @@ def philox():
     print("philox_ref.npz", len(out))
 
 
+def prompt_attention():
+    import importlib.util
+    import json
+    import random
+    import warnings
+
+    warnings.simplefilter("ignore")
+    spec = importlib.util.spec_from_file_location("ref_prompt_parser", "/root/reference/modules/prompt_parser.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)  # the reference's module, unmodified
+    prompts = ["", "normal text", "an (important) word", "(unbalanced", r"\(literal\]", "(unnecessary)(parens)",
+               "a (((house:1.3)) [on] a (hill:0.5), sun, (((sky))).", "a cat BREAK a dog", "(a BREAK b:1.4) c", "x BREAKING y",
+               "[[deep] er] and ((more:0.25) text)", "colon: alone :1.2) ) ] closing", "(neg:-0.5) (sp : 1.5 ) (plus:+2)",
+               r"back\\slash \ lone \x", "masterpiece, (best quality:1.2), [lowres], ((detailed face)), 8k",
+               "(((", "]]]", "(a:1.1", "(a:)", "a:b:c", "(::1.5)", "[a:b:0.5]", "((x):2)(y:3)", " lead and trail "]
+    rnd = random.Random(7)
+    alphabet = ["(", ")", "[", "]", ":", "\\", " ", "a", "bc", "1.2", ".5", "BREAK", ",", "-", "+"]
+    for _ in range(300):
+        prompts.append("".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 24))))
+    out = []
+    for p in prompts:
+        try:
+            out.append({"prompt": p, "result": ref.parse_prompt_attention(p)})
+        except Exception as e:  # e.g. float("..") — the restatement must fail the same way
+            out.append({"prompt": p, "error": type(e).__name__})
+    with open(os.path.join(HERE, "prompt_attention.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("prompt_attention.json", len(out), sum(1 for o in out if "error" in o), "error cases")
+
+
 def tiny():
     from oracle.pipeline import OraclePipeline, SamplingParams
     from oracle.synth import init_module_, synthetic_context
@@ -60,4 +92,5 @@ def tiny():
 
 if __name__ == "__main__":
     philox()
+    prompt_attention()
     tiny()

@@ -160,3 +160,27 @@ def test_shard_indices_partition():
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     assert shard(list(range(10, 18)), 1, 4) == [12, 13]
     assert torch.equal(shard(torch.arange(8), 3, 4), torch.tensor([6, 7]))
+
+
+def test_prompt_attention_matches_reference_golden():
+    """sdwebui_b200.prompt_parser.parse_prompt_attention == modules/prompt_parser.py:370-458 on every golden prompt
+    (hand-written cases incl. the reference's own doctest examples, plus 300 fuzzed strings; generator:
+    tests/golden/make_golden.py, which imports the reference module from /root/reference)."""
+    import json
+    import os
+
+    from sdwebui_b200.prompt_parser import parse_prompt_attention
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "prompt_attention.json")) as f:
+        cases = json.load(f)
+    assert len(cases) > 300
+    for c in cases:
+        if "error" in c:
+            try:
+                parse_prompt_attention(c["prompt"])
+            except Exception as e:  # noqa: BLE001
+                assert type(e).__name__ == c["error"], (c["prompt"], type(e).__name__, c["error"])
+            else:
+                raise AssertionError(f"expected {c['error']} for {c['prompt']!r}")
+        else:
+            assert parse_prompt_attention(c["prompt"]) == c["result"], c["prompt"]
