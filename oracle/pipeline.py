@@ -134,9 +134,10 @@ class OraclePipeline:
 
 
 def psnr_uint8(a: torch.Tensor, b: torch.Tensor) -> float:
-    """PSNR (dB) on uint8 RGB as the webui would save it (x*255 rounded, modules/processing.py:1017-1018)."""
-    a8 = (a.float() * 255.0).round().clamp(0, 255)
-    b8 = (b.float() * 255.0).round().clamp(0, 255)
+    """PSNR (dB) on uint8 RGB as the webui would save it: `255. * x` then `astype(np.uint8)`, which truncates
+    (modules/processing.py:1034-1035)."""
+    a8 = (a.float() * 255.0).clamp(0, 255).floor()
+    b8 = (b.float() * 255.0).clamp(0, 255).floor()
     mse = ((a8 - b8) ** 2).mean().item()
     if mse == 0:
         return float("inf")

@@ -122,6 +122,7 @@ class CrossAttention(nn.Module):
         inner = heads * dim_head
         context_dim = context_dim or query_dim
         self.heads = heads
+        self.scale = dim_head ** -0.5  # ldm attribute the non-SDP reference forwards read (sd_hijack_optimizations.py:236)
         self.to_q = nn.Linear(query_dim, inner, bias=False)
         self.to_k = nn.Linear(context_dim, inner, bias=False)
         self.to_v = nn.Linear(context_dim, inner, bias=False)

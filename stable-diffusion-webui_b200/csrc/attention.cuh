@@ -21,6 +21,7 @@ struct alignas(64) AttnArgs {
   void* out;        // [B*Nq, ldo] 16-bit; head h writes columns out_col0 + h*dv ...
   int ldo;
   int out_col0;
+  int dbg;          // knockout experiments (SDXE_ATT_KO), 0 in production
 };
 
 int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);

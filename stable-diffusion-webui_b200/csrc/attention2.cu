@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         if (elect_one()) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            if (c < QS) {
+            if (c < QS && !(a.dbg & 128)) {
               const int ks = (c == QS - 1) ? ksteps_last : 4;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         if (elect_one()) {
 #pragma unroll
           for (int vs = 0; vs < 2; ++vs) {
-            if (vs < VS) {
+            if (vs < VS && !(a.dbg & 64)) {
               const uint32_t d_o = tmem_base + 256u + (uint32_t)(t * 128 + vs * 64);
               const uint32_t id = (vs == VS - 1) ? idesc_pv_last : idesc_pv;
 #pragma unroll
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
     const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + quarter);               // the two warps sharing these 32 rows
     float* xq = xch + t * 256;                                                 // [2 buf][2 tiles][2 halves][128]
     const float sl2 = a.scale_log2;
+    const int ko = a.dbg;
     float m_run = -INFINITY, l_run = 0.f;
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(s_full(t), (uint32_t)(i & 1));
@@ -255,14 +256,19 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
-          tc_wait_ld();
+          if (!(ko & 8)) {
+            tmem_ld32(t_s + c * 32, r);
+            tc_wait_ld();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(-1.f - 0.01f * j);
+          }
           if (tail) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (kv0 + c * 32 + j >= a.Nk) r[j] = 0xff800000u;  // -inf
           }
-          if (with_max) {
+          if (with_max && !(ko & 16)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               mx0 = fmaxf(mx0, __uint_as_float(r[j]));
@@ -273,17 +279,29 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb));
-            const float p4 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb));
-            const float p5 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb));
-            const float p6 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb));
-            const float p7 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb));
+            float p0, p1, p2, p3, p4, p5, p6, p7;
+            if (!(ko & 1)) {
+              p0 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb));
+              p1 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb));
+              p2 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb));
+              p3 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb));
+              p4 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb));
+              p5 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb));
+              p6 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb));
+              p7 = ex2_approx(fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb));
+            } else {
+              p0 = fmaf(__uint_as_float(r[q * 8 + 0]), sl2, -mb);
+              p1 = fmaf(__uint_as_float(r[q * 8 + 1]), sl2, -mb);
+              p2 = fmaf(__uint_as_float(r[q * 8 + 2]), sl2, -mb);
+              p3 = fmaf(__uint_as_float(r[q * 8 + 3]), sl2, -mb);
+              p4 = fmaf(__uint_as_float(r[q * 8 + 4]), sl2, -mb);
+              p5 = fmaf(__uint_as_float(r[q * 8 + 5]), sl2, -mb);
+              p6 = fmaf(__uint_as_float(r[q * 8 + 6]), sl2, -mb);
+              p7 = fmaf(__uint_as_float(r[q * 8 + 7]), sl2, -mb);
+            }
             s0 += p0 + p1; s1 += p2 + p3; s2 += p4 + p5; s3 += p6 + p7;
             const uint32_t chunk = (uint32_t)(c * 4 + q) ^ (uint32_t)(row & 7);  // 16-byte chunk of this row, 128B swizzle
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+            if (!(ko & 2)) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
                          "r"(T::pack(p0, p1)), "r"(T::pack(p2, p3)), "r"(T::pack(p4, p5)), "r"(T::pack(p6, p7))
                          : "memory");
           }
@@ -295,11 +313,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // agree on the row max with the thread that owns the other 64 columns
       float* xb = xq + (i & 1) * 512;
-      xb[half * 128 + row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+      if (!(ko & 4)) {
+        xb[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+      }
       const float m_cand = fmaxf(m_run, mx);
-      const bool need = (m_cand - m_run) * sl2 > 8.f;  // first block: +inf > 8
+      const bool need = (ko & 32) ? (i == 0) : ((m_cand - m_run) * sl2 > 8.f);  // first block: +inf > 8
       if (__any_sync(0xffffffffu, need)) {  // same rows, same decision in both warps of the pair
         const float alpha = ex2_approx((m_run - m_cand) * sl2);
         if (i >= 1) {
@@ -383,6 +403,11 @@ int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   AttnArgs a = a_in;
   const int budget = (224 * 1024 - 2048) / SLAB2;  // 13 slabs
   a.q_resident = 1;
+  {
+    static int ko = -1;
+    if (ko < 0) { const char* e = getenv("SDXE_ATT_KO"); ko = e ? atoi(e) : 0; }
+    a.dbg = ko;
+  }
   a.num_slots = std::min(10, budget - 4 - 2 * a.dqk_slabs);
   if (a.num_slots < a.dqk_slabs + a.dv_slabs + 1) { set_last_error(__FILE__, __LINE__, "attention2: smem"); return -1; }
   const size_t smem = (size_t)(2 * a.dqk_slabs + a.num_slots + 4) * SLAB2 + 8 * (2 * a.num_slots + 7) + 16 + 4096 + 1024;

@@ -39,8 +39,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
     if bias is not None:
         bias = bias.float().contiguous()
     flags = (1 if geglu else 0) | (force_bn << 8)
-    L.check(L.load().sdxe_gemm(L.ptr(a.contiguous()), L.ptr(w.contiguous()), L.ptr(out), M, N, K, L.ptr(bias),
-                               L.ptr(residual), flags, L.torch_dtype_code(a.dtype), L.current_stream()), "sdxe_gemm")
+    # every converted tensor is bound to a local that outlives the C call: a temporary passed straight into L.ptr()
+    # is freed on return from ptr() and the caching allocator may hand its block to the next temporary
+    a_c, w_c = a.contiguous(), w.contiguous()
+    res_c = residual.contiguous() if residual is not None else None
+    L.check(L.load().sdxe_gemm(L.ptr(a_c), L.ptr(w_c), L.ptr(out), M, N, K, L.ptr(bias),
+                               L.ptr(res_c), flags, L.torch_dtype_code(a.dtype), L.current_stream()), "sdxe_gemm")
+    del a_c, w_c, res_c
     return out
 
 
@@ -53,8 +58,10 @@ def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = N
     out = torch.empty(n, h, wd, cout, dtype=x.dtype, device=x.device)
     if bias is not None:
         bias = bias.float().contiguous()
-    L.check(L.load().sdxe_conv3x3_nhwc(L.ptr(x.contiguous()), L.ptr(wp), L.ptr(out), n, h, wd, cin, cout, L.ptr(bias),
+    x_c = x.contiguous()
+    L.check(L.load().sdxe_conv3x3_nhwc(L.ptr(x_c), L.ptr(wp), L.ptr(out), n, h, wd, cin, cout, L.ptr(bias),
                                        L.torch_dtype_code(x.dtype), L.current_stream()), "sdxe_conv3x3_nhwc")
+    del x_c
     return out
 
 
@@ -62,11 +69,12 @@ def group_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gr
                     silu: bool = False) -> torch.Tensor:
     _require_cuda(x)
     n, h, wd, c = x.shape
-    out = torch.empty_like(x)
-    L.check(L.load().sdxe_group_norm_nhwc(L.ptr(x.contiguous()), L.ptr(gamma.float().contiguous()),
-                                          L.ptr(beta.float().contiguous()), L.ptr(out), n, h * wd, c, groups, eps,
+    x_c, g, b = x.contiguous(), gamma.float().contiguous(), beta.float().contiguous()
+    out = torch.empty_like(x_c)
+    L.check(L.load().sdxe_group_norm_nhwc(L.ptr(x_c), L.ptr(g), L.ptr(b), L.ptr(out), n, h * wd, c, groups, eps,
                                           1 if silu else 0, L.torch_dtype_code(x.dtype), L.current_stream()),
             "sdxe_group_norm_nhwc")
+    del x_c, g, b
     return out
 
 
@@ -74,8 +82,9 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     _require_cuda(x)
     c = x.shape[-1]
     rows = x.numel() // c
-    out = torch.empty_like(x)
-    L.check(L.load().sdxe_layer_norm(L.ptr(x.contiguous()), L.ptr(gamma.float().contiguous()),
-                                     L.ptr(beta.float().contiguous()), L.ptr(out), rows, c, eps,
+    x_c, g, b = x.contiguous(), gamma.float().contiguous(), beta.float().contiguous()
+    out = torch.empty_like(x_c)
+    L.check(L.load().sdxe_layer_norm(L.ptr(x_c), L.ptr(g), L.ptr(b), L.ptr(out), rows, c, eps,
                                      L.torch_dtype_code(x.dtype), L.current_stream()), "sdxe_layer_norm")
+    del x_c, g, b
     return out

@@ -102,11 +102,17 @@ class StableDiffusionProcessingTxt2Img:
     s_noise: float = 1.0
     s_min_uncond: float = 0.0
     randn_source: str = "GPU"
+    subseeds: Optional[List[int]] = None     # modules/processing.py:949 — variation seeds, slerp-ed in at subseed_strength
+    subseed_strength: float = 0.0
+    seed_resize_from_h: int = 0
+    seed_resize_from_w: int = 0
+    eta_noise_seed_delta: int = 0            # opts.eta_noise_seed_delta (modules/rng.py:148-150)
     enable_hr: bool = False
     hr_scale: float = 2.0
     hr_second_pass_steps: int = 0
     denoising_strength: float = 0.75
     do_not_decode: bool = False
+    check_for_nans: bool = True      # the reference checks unless --disable-nan-check (modules/devices.py:229-231)
     batch_size: int = 0
     rng: ImageRNG = None
     sampler: S.KDiffusionSampler = None
@@ -114,6 +120,11 @@ class StableDiffusionProcessingTxt2Img:
 
     def __post_init__(self):
         self.batch_size = len(self.seeds)
+
+    def make_rng(self, shape, seeds) -> ImageRNG:
+        return ImageRNG(shape, seeds, subseeds=self.subseeds, subseed_strength=self.subseed_strength,
+                        seed_resize_from_h=self.seed_resize_from_h, seed_resize_from_w=self.seed_resize_from_w,
+                        source=self.randn_source, device=self.sd_model.device, eta_noise_seed_delta=self.eta_noise_seed_delta)
 
     # modules/processing.py:1307-1362
     def sample(self, conditioning, unconditional_conditioning, seeds):
@@ -130,7 +141,7 @@ class StableDiffusionProcessingTxt2Img:
         tw, th = int(self.width * self.hr_scale), int(self.height * self.hr_scale)
         samples = torch.nn.functional.interpolate(samples, size=(th // opt_f, tw // opt_f), mode="bilinear", antialias=False)
         shape = (opt_C, th // opt_f, tw // opt_f)
-        self.rng = ImageRNG(shape, seeds, source=self.randn_source, device=self.sd_model.device)
+        self.rng = self.make_rng(shape, seeds)                                     # processing.py:1429
         noise = self.rng.next()
         self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
         return self.sampler.sample_img2img(self, samples, noise, self.c, self.uc, steps=self.hr_second_pass_steps or self.steps)
@@ -189,17 +200,36 @@ class Processed:
     seeds: List[int] = None
 
 
+class NansException(Exception):
+    """modules/devices.py:237-238."""
+
+
+def test_for_nans(x: torch.Tensor, where: str):
+    """modules/devices.py:241-265: the probe reads ONE element, `x[(0,) * x.ndim]` (a NaN anywhere in a UNet / VAE
+    output spreads to the whole tensor through the next norm or attention), and raises NansException."""
+    probe = x[(0,) * x.ndim] if x.ndim else x
+    if not bool(torch.isnan(probe)):
+        return
+    if where == "unet":
+        msg = "A tensor with NaNs was produced in Unet."
+    elif where == "vae":
+        msg = "A tensor with NaNs was produced in VAE."
+    else:
+        msg = "A tensor with NaNs was produced."
+    raise NansException(msg + " Use --disable-nan-check commandline argument to disable this check.")
+
+
 def decode_latent_batch(model: SdModel, batch: torch.Tensor, target_device=None, check_for_nans=False, batched=True):
-    """modules/processing.py:625-672. The reference decodes one image at a time; the engine takes the whole batch in
-    one call (`batched=True`) — per-sample GroupNorm/attention make the results identical either way."""
-    if check_for_nans and bool(torch.isnan(batch.view(-1)[0])):
-        raise L.SdxeError("A tensor with all NaNs was produced in Unet.")  # devices.test_for_nans contract
+    """modules/processing.py:625-672. The reference decodes one image at a time and probes each decoded image
+    (:637-641); the engine takes the whole batch in one call (`batched=True`; per-sample GroupNorm / attention make the
+    results identical either way) and probes the first element of every image with one host read. The reference's
+    NaN -> fp32-VAE retry (:643-665, opt-in via auto_vae_precision) stays upstream of the engine."""
     if batched:
         out = model.decode_first_stage(batch)
     else:
         out = torch.cat([model.decode_first_stage(batch[i:i + 1]) for i in range(batch.shape[0])])
-    if check_for_nans and bool(torch.isnan(out.view(-1)[0])):
-        raise L.SdxeError("A tensor with all NaNs was produced in VAE.")
+    if check_for_nans and bool(torch.isnan(out[:, 0, 0, 0]).any()):
+        test_for_nans(out[int(torch.isnan(out[:, 0, 0, 0]).nonzero()[0])], "vae")
     return out if target_device is None else out.to(target_device)
 
 
@@ -210,13 +240,16 @@ def process_images(p: StableDiffusionProcessingTxt2Img, to_host: bool = True) ->
     S.state.skipped = False
     dev = p.sd_model.device
     with torch.cuda.device(dev):
-        p.rng = ImageRNG((opt_C, p.height // opt_f, p.width // opt_f), p.seeds, source=p.randn_source, device=dev)
+        p.rng = p.make_rng((opt_C, p.height // opt_f, p.width // opt_f), p.seeds)           # processing.py:949
         samples = p.sample(p.c, p.uc, p.seeds)
         if p.do_not_decode:
             return Processed(None, samples, list(p.seeds))
-        x = decode_latent_batch(p.sd_model, samples, check_for_nans=False)
-        x = torch.clamp((x.float() + 1.0) / 2.0, min=0.0, max=1.0)                         # processing.py:1004-1005
-        img = (x.permute(0, 2, 3, 1) * 255.0).round().clamp(0, 255).to(torch.uint8)        # :1017-1018
+        if p.check_for_nans:  # devices.test_for_nans(samples_ddim, "unet"), processing.py:998 (on unless --disable-nan-check)
+            test_for_nans(samples, "unet")
+        x = decode_latent_batch(p.sd_model, samples, check_for_nans=p.check_for_nans)      # :1002
+        x = torch.clamp((x.float() + 1.0) / 2.0, min=0.0, max=1.0)                         # :1004-1005
+        # :1034-1035 `x_sample = 255. * ...; x_sample.astype(np.uint8)` — numpy's float -> uint8 cast TRUNCATES
+        img = (x.permute(0, 2, 3, 1) * 255.0).to(torch.uint8)
         if not to_host:
             return Processed(img, samples, list(p.seeds))
         host = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)

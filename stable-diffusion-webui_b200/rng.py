@@ -53,36 +53,96 @@ class PhiloxGenerator:
         return out
 
 
+def slerp(val, low, high):
+    """modules/rng.py:85-96, verbatim semantics — including its quirks on [C,h,w] inputs (norms and dot products run
+    over dim 1, and nearly parallel inputs fall back to `low * val + high * (1 - val)`)."""
+    low_norm = low / torch.norm(low, dim=1, keepdim=True)
+    high_norm = high / torch.norm(high, dim=1, keepdim=True)
+    dot = (low_norm * high_norm).sum(1)
+    if dot.mean() > 0.9995:
+        return low * val + high * (1 - val)
+    omega = torch.acos(dot)
+    so = torch.sin(omega)
+    return (torch.sin((1.0 - val) * omega) / so).unsqueeze(1) * low + (torch.sin(val * omega) / so).unsqueeze(1) * high
+
+
 class ImageRNG:
-    """`first()` = the initial latent noise, `next()` = per-step ancestral noise; both stack per-image draws.
-    Subseed slerp / seed-resize (modules/rng.py:113-146) are not on the benchmarked path and raise if requested."""
+    """modules/rng.py:99-163. `first()` = the initial latent noise (with the reference's subseed slerp, seed-resize paste
+    and eta-noise-seed-delta), `next()` = per-step ancestral noise; both stack per-image draws.
+
+    The reference's `randn(seed, shape)` seeds the GLOBAL generator and draws from it; here a fresh generator seeded with
+    `seed` produces the same numbers, and (source != "NV") the global torch seed is set as well so that code running
+    after the webui's ImageRNG sees the same global state (`mirror_global_seed`)."""
 
     def __init__(self, shape, seeds, subseeds=None, subseed_strength=0.0, seed_resize_from_h=0, seed_resize_from_w=0,
-                 source: str = "GPU", device="cuda:0"):
-        if (subseeds is not None and subseed_strength != 0) or seed_resize_from_h > 0 or seed_resize_from_w > 0:
-            raise NotImplementedError("subseed / seed-resize noise is outside the accelerated path")
+                 source: str = "GPU", device="cuda:0", eta_noise_seed_delta: int = 0, mirror_global_seed: bool = True):
         self.shape = tuple(int(s) for s in shape)
         self.seeds = [int(s) for s in seeds]
+        self.subseeds = None if subseeds is None else [int(s) for s in subseeds]
+        self.subseed_strength = subseed_strength
+        self.seed_resize_from_h = seed_resize_from_h
+        self.seed_resize_from_w = seed_resize_from_w
+        self.eta_noise_seed_delta = int(eta_noise_seed_delta or 0)
+        self.mirror_global_seed = mirror_global_seed
         self.source = source
         self.device = torch.device(device)
-        if source == "NV":
-            self.generators = [PhiloxGenerator(s) for s in self.seeds]
-        else:
-            gdev = self.device if source == "GPU" else torch.device("cpu")
-            self.generators = [torch.Generator(gdev).manual_seed(s) for s in self.seeds]
+        self.generators = [self._create_generator(s) for s in self.seeds]
         self.is_first = True
 
-    def _draw(self, g) -> torch.Tensor:
+    # modules/rng.py:75-82
+    def _create_generator(self, seed):
         if self.source == "NV":
-            return torch.from_numpy(g.randn(self.shape)).to(self.device, non_blocking=True)
+            return PhiloxGenerator(seed)
         gdev = self.device if self.source == "GPU" else torch.device("cpu")
-        return torch.randn(self.shape, device=gdev, generator=g).to(self.device)
+        return torch.Generator(gdev).manual_seed(int(seed))
+
+    def _draw(self, g, shape=None) -> torch.Tensor:
+        shape = self.shape if shape is None else shape
+        if self.source == "NV":
+            return torch.from_numpy(g.randn(shape)).to(self.device, non_blocking=True)
+        gdev = self.device if self.source == "GPU" else torch.device("cpu")
+        return torch.randn(shape, device=gdev, generator=g).to(self.device)
+
+    # modules/rng.py:6-19: manual_seed(seed), then draw from `generator` or from the freshly seeded global one
+    def _randn(self, seed, shape, generator=None) -> torch.Tensor:
+        if self.source != "NV" and self.mirror_global_seed:
+            torch.manual_seed(int(seed))
+        return self._draw(generator if generator is not None else self._create_generator(seed), shape)
 
     def first(self) -> torch.Tensor:
-        return torch.stack([self._draw(g) for g in self.generators])
+        resize = self.seed_resize_from_h > 0 and self.seed_resize_from_w > 0
+        noise_shape = (self.shape[0], int(self.seed_resize_from_h) // 8, int(self.seed_resize_from_w // 8)) if resize else self.shape
+        xs = []
+        for i, (seed, generator) in enumerate(zip(self.seeds, self.generators)):
+            subnoise = None
+            if self.subseeds is not None and self.subseed_strength != 0:
+                subseed = 0 if i >= len(self.subseeds) else self.subseeds[i]
+                subnoise = self._randn(subseed, noise_shape)
+            if noise_shape != self.shape:
+                noise = self._randn(seed, noise_shape)
+            else:
+                noise = self._randn(seed, self.shape, generator=generator)
+            if subnoise is not None:
+                noise = slerp(self.subseed_strength, noise, subnoise)
+            if noise_shape != self.shape:  # paste the centre of the source-resolution noise into fresh target noise
+                x = self._randn(seed, self.shape, generator=generator)
+                dx = (self.shape[2] - noise_shape[2]) // 2
+                dy = (self.shape[1] - noise_shape[1]) // 2
+                w = noise_shape[2] if dx >= 0 else noise_shape[2] + 2 * dx
+                h = noise_shape[1] if dy >= 0 else noise_shape[1] + 2 * dy
+                tx = 0 if dx < 0 else dx
+                ty = 0 if dy < 0 else dy
+                dx = max(-dx, 0)
+                dy = max(-dy, 0)
+                x[:, ty:ty + h, tx:tx + w] = noise[:, dy:dy + h, dx:dx + w]
+                noise = x
+            xs.append(noise)
+        if self.eta_noise_seed_delta:
+            self.generators = [self._create_generator(seed + self.eta_noise_seed_delta) for seed in self.seeds]
+        return torch.stack(xs).to(self.device)
 
     def next(self) -> torch.Tensor:
         if self.is_first:
             self.is_first = False
             return self.first()
-        return torch.stack([self._draw(g) for g in self.generators])
+        return torch.stack([self._draw(g) for g in self.generators]).to(self.device)
