@@ -132,6 +132,14 @@ int sdxe_denoiser_in(const float* x, const int32_t* src, const float* c_in, void
  * common one-cond-per-image case: rows [0,B) cond, [B,2B) uncond. eps is 16-bit or fp32. */
 int sdxe_cfg_combine(const float* x, const void* eps, const float* sigma, float cond_scale, float* denoised, int B,
                      int64_t elems, int eps_dtype, void* stream);
+/* General form of the same combine (AND-composed prompts, per-cond weights): image b owns eps rows
+ * cond_rows[row_ptr[b] .. row_ptr[b+1]) with weights cond_w[k] (= weight_k * cond_scale) and uncond row uncond_rows[b]
+ * (when the uncond pass is skipped, s_min_uncond, the reference substitutes the image's first cond row, :272-275):
+ * denoised[b] = den_u + sum_k cond_w[k] * (den_k - den_u), den_r = x[b] + eps[r] * (-sigma[b]).
+ * row_ptr: int32[B+1], cond_rows: int32[nnz], cond_w: fp32[nnz], uncond_rows: int32[B] (device). */
+int sdxe_cfg_combine_multi(const float* x, const void* eps, const float* sigma, const int32_t* row_ptr,
+                           const int32_t* cond_rows, const float* cond_w, const int32_t* uncond_rows, float* denoised,
+                           int B, int64_t elems, int eps_dtype, void* stream);
 /* x <- x + (x - denoised)/sigma * (sigma_down - sigma) + noise * sigma_up  (noise may be NULL when sigma_up == 0). */
 int sdxe_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma, float sigma_down,
                               float sigma_up, int64_t total, void* stream);

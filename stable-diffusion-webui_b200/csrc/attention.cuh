@@ -22,6 +22,7 @@ struct alignas(64) AttnArgs {
   int ldo;
   int out_col0;
   int dbg;          // knockout experiments (SDXE_ATT_KO), 0 in production
+  unsigned long long* trace;  // timeline of CTA (0,0) (SDXE_ATT_TRACE), null in production
 };
 
 int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);

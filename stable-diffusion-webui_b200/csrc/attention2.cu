@@ -48,6 +48,15 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
   float* xch = reinterpret_cast<float*>(smem + (bar_base - sbase) + 8 * (2 * NS + 7) + 16);  // row max / sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // timeline trace (debug): slot layout [role 0..3][iteration 0..47][event 0..7]
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto TR = [&](int role, int it, int ev) {
+    if (tracing && lane == 0 && it < 48) {
+      unsigned long long c;
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+      a.trace[(role * 48 + it) * 8 + ev] = c;
+    }
+  };
   const int q0 = blockIdx.x * 256;
   const int bh = blockIdx.y;
   const int hb_b = bh / a.H, hb_h = bh - hb_b * a.H;  // (batch, head) coordinates of the 4D per-head tensor maps
@@ -95,8 +104,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       for (int i = 0; i <= nblk; ++i) {
         if (i < nblk)
           for (int c = 0; c < QS; ++c) push(&a.tmK, c * 64, i * 128);
+        TR(3, i, 0);
         if (i >= 1)
           for (int vs = 0; vs < VS; ++vs) push(&a.tmV, vs * 64, (i - 1) * 128);
+        TR(3, i, 1);
       }
     }
   } else if (warp == 1) {
@@ -181,6 +192,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       release(k_slot, QS);
       for (int i = 0; i < nblk; ++i) {
         const bool more = i + 1 < nblk;
+        TR(2, i, 0);
         if (more) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
@@ -189,21 +201,26 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
 #pragma unroll
         for (int vs = 0; vs < 2; ++vs)
           if (vs < VS) vd[vs] = umma_desc_sw128(pop(v_slot[vs]), SLAB2, 1024);
+        TR(2, i, 1);
         // the two tiles are served in ARRIVAL order (a tile that finishes its softmax first must not wait for the
         // other one's p_ready: that is what lets the tiles drift half a period apart and alternate on the MUFU pipe)
         {
           bool served0 = false, served1 = false;
           for (uint32_t spin = 0; !(served0 && served1); ++spin) {
             if (!served0 && __any_sync(0xffffffffu, mbar_test(p_ready(0), (uint32_t)(i & 1)))) {
+              TR(2, i, 2);
               tc_fence_after();
               if (more) issue_s(0);
               issue_pv(0, i);
+              TR(2, i, 3);
               served0 = true;
             }
             if (!served1 && __any_sync(0xffffffffu, mbar_test(p_ready(1), (uint32_t)(i & 1)))) {
+              TR(2, i, 4);
               tc_fence_after();
               if (more) issue_s(1);
               issue_pv(1, i);
+              TR(2, i, 5);
               served1 = true;
             }
             if (spin > (1u << 28)) {
@@ -236,9 +253,12 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
     const float sl2 = a.scale_log2;
     const int ko = a.dbg;
     float m_run = -INFINITY, l_run = 0.f;
+    const bool trw = half == 0 && quarter == 0;
     for (int i = 0; i < nblk; ++i) {
+      if (trw) TR(t, i, 0);
       mbar_wait(s_full(t), (uint32_t)(i & 1));
       tc_fence_after();
+      if (trw) TR(t, i, 1);
       const int kv0 = i * 128 + half * 64;
       const bool tail = kv0 + 64 > a.Nk;  // only the last block has invalid key columns
       if (i >= 1) {
@@ -309,7 +329,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       };
       // speculative pass against the stale max (first block: m_run = -inf -> mb = -inf -> p = inf/NaN garbage that the
       // mandatory redo below overwrites; the sums are recomputed by the redo as well)
+      if (trw) TR(t, i, 2);
       pass(i == 0 ? 0.f : m_run * sl2, true);
+      if (trw) TR(t, i, 3);
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // agree on the row max with the thread that owns the other 64 columns
       float* xb = xq + (i & 1) * 512;
@@ -338,10 +360,12 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
         pass(m_run * sl2, false);  // redo this block against the new max
       }
       l_run += (s0 + s1) + (s2 + s3);
+      if (trw) TR(t, i, 4);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(t));
+      if (trw) TR(t, i, 5);
     }
     // ---- epilogue: the row sum is the sum of the two halves' partial sums
     {
@@ -408,6 +432,15 @@ int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
     if (ko < 0) { const char* e = getenv("SDXE_ATT_KO"); ko = e ? atoi(e) : 0; }
     a.dbg = ko;
   }
+  static unsigned long long* trace_buf = nullptr;
+  static int trace_mode = -1;
+  if (trace_mode < 0) { const char* e = getenv("SDXE_ATT_TRACE"); trace_mode = e ? atoi(e) : 0; }
+  a.trace = nullptr;
+  if (trace_mode == 1) {
+    if (!trace_buf) { cudaMalloc(&trace_buf, 4 * 48 * 8 * 8); }
+    cudaMemsetAsync(trace_buf, 0, 4 * 48 * 8 * 8, stream);
+    a.trace = trace_buf;
+  }
   a.num_slots = std::min(10, budget - 4 - 2 * a.dqk_slabs);
   if (a.num_slots < a.dqk_slabs + a.dv_slabs + 1) { set_last_error(__FILE__, __LINE__, "attention2: smem"); return -1; }
   const size_t smem = (size_t)(2 * a.dqk_slabs + a.num_slots + 4) * SLAB2 + 8 * (2 * a.num_slots + 7) + 16 + 4096 + 1024;
@@ -415,6 +448,24 @@ int attention2_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   auto kern = bf16 ? attention2_kernel<true> : attention2_kernel<false>;
   dim3 grid((a.Nq + 255) / 256, a.B * a.H);
   SDXE_CUDA_CHECK(launch_k(kern, grid, dim3(ATT2_THREADS), smem, stream, a));
+  if (trace_mode == 1) {
+    trace_mode = 2;  // once
+    cudaStreamSynchronize(stream);
+    static unsigned long long h[4 * 48 * 8];
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    FILE* f = fopen("gpurun_out/attn_trace.txt", "w");
+    if (f) {
+      unsigned long long t0 = ~0ull;
+      for (auto v : h) if (v && v < t0) t0 = v;
+      for (int role = 0; role < 4; ++role)
+        for (int it = 0; it < 48; ++it) {
+          fprintf(f, "role %d it %2d:", role, it);
+          for (int ev = 0; ev < 8; ++ev) fprintf(f, " %8lld", h[(role * 48 + it) * 8 + ev] ? (long long)(h[(role * 48 + it) * 8 + ev] - t0) : -1ll);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
   return 0;
 }
 

@@ -142,6 +142,12 @@ int sdxe_cfg_combine(const float* x, const void* eps, const float* sigma, float 
                      int64_t elems, int eps_dtype, void* stream) {
   return cfg_combine_launch(x, eps, sigma, cond_scale, denoised, B, elems, eps_dtype, (cudaStream_t)stream);
 }
+int sdxe_cfg_combine_multi(const float* x, const void* eps, const float* sigma, const int32_t* row_ptr,
+                           const int32_t* cond_rows, const float* cond_w, const int32_t* uncond_rows, float* denoised,
+                           int B, int64_t elems, int eps_dtype, void* stream) {
+  return cfg_combine_multi_launch(x, eps, sigma, row_ptr, cond_rows, cond_w, uncond_rows, denoised, B, elems, eps_dtype,
+                                  (cudaStream_t)stream);
+}
 int sdxe_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma, float sigma_down,
                               float sigma_up, int64_t total, void* stream) {
   return euler_a_step_launch(x, denoised, noise, sigma, sigma_down, sigma_up, total, (cudaStream_t)stream);

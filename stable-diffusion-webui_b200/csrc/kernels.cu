@@ -836,6 +836,39 @@ int cfg_combine_launch(const float* x, const void* eps, const float* sigma, floa
   return 0;
 }
 
+// General CFG combine (sd_samplers_cfg_denoiser.py:74-82 with an arbitrary conds_list): image b owns the cond rows
+// cond_rows[row_ptr[b] .. row_ptr[b+1]) of eps with weights cond_w[...] (already multiplied by cond_scale) and the uncond
+// row uncond_row0 + b.  den_r = x_b + eps_r * (-sigma_b);  out_b = den_u + sum_k w_k (den_k - den_u).
+__global__ void cfg_combine_multi_kernel(const float* __restrict__ x, const void* __restrict__ eps,
+                                         const float* __restrict__ sigma, const int32_t* __restrict__ row_ptr,
+                                         const int32_t* __restrict__ cond_rows, const float* __restrict__ cond_w,
+                                         const int32_t* __restrict__ uncond_rows, float* __restrict__ out, int B,
+                                         int64_t elems, int eps_dtype) {
+  const int64_t total = B * elems;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / elems);
+    const int64_t e = idx - b * elems;
+    const float xv = x[idx], c_out = -sigma[b];
+    const float du = xv + load_any(eps, eps_dtype, (int64_t)uncond_rows[b] * elems + e) * c_out;
+    float acc = du;
+    for (int k = row_ptr[b]; k < row_ptr[b + 1]; ++k) {
+      const float dc = xv + load_any(eps, eps_dtype, (int64_t)cond_rows[k] * elems + e) * c_out;
+      acc += (dc - du) * cond_w[k];
+    }
+    out[idx] = acc;
+  }
+}
+
+int cfg_combine_multi_launch(const float* x, const void* eps, const float* sigma, const int32_t* row_ptr,
+                             const int32_t* cond_rows, const float* cond_w, const int32_t* uncond_rows, float* denoised,
+                             int B, int64_t elems, int eps_dtype, cudaStream_t s) {
+  const int64_t total = B * elems;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  cfg_combine_multi_kernel<<<blocks, 256, 0, s>>>(x, eps, sigma, row_ptr, cond_rows, cond_w, uncond_rows, denoised, B, elems, eps_dtype);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void euler_a_step_kernel(float* __restrict__ x, const float* __restrict__ den, const float* __restrict__ noise,
                                     float inv_sigma, float dt, float sigma_up, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

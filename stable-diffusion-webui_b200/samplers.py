@@ -125,10 +125,46 @@ def _cond_tensor(c):
     return c["crossattn"] if isinstance(c, dict) else c
 
 
+def catenate_conds(conds):
+    """sd_samplers_cfg_denoiser.py:11-15."""
+    if not isinstance(conds[0], dict):
+        return torch.cat(conds)
+    return {key: torch.cat([x[key] for x in conds]) for key in conds[0].keys()}
+
+
+def subscript_cond(cond, a, b):
+    """sd_samplers_cfg_denoiser.py:18-22."""
+    if not isinstance(cond, dict):
+        return cond[a:b]
+    return {key: vec[a:b] for key, vec in cond.items()}
+
+
+def pad_cond(tensor, repeats, empty):
+    """sd_samplers_cfg_denoiser.py:25-30: append `repeats` copies of the empty-prompt embedding along the token axis."""
+    if not isinstance(tensor, dict):
+        return torch.cat([tensor, empty.repeat((tensor.shape[0], repeats, 1))], axis=1)
+    tensor["crossattn"] = pad_cond(tensor["crossattn"], repeats, empty)
+    return tensor
+
+
+class CFGDenoiserOptions:
+    """The `shared.opts` fields CFGDenoiser.forward reads (defaults: modules/shared_options.py)."""
+
+    batch_cond_uncond = True
+    pad_cond_uncond = False
+    pad_cond_uncond_v0 = False
+    s_min_uncond_all = False
+    skip_early_cond = 0.0
+
+
 class CFGDenoiser:
-    """Classifier-free-guidance denoiser with the reference's call signature. `cond` / `uncond` are the per-step
-    reconstructed conditionings: a tensor [B, T, C] or, for SDXL, a dict {"crossattn": [B,T,C], "vector": [B,2816]}
-    (what prompt_parser.reconstruct_*_batch returns, modules/prompt_parser.py:280-349). One cond per image."""
+    """Classifier-free-guidance denoiser with the reference's call signature and batching rules
+    (modules/sd_samplers_cfg_denoiser.py:156-311).
+
+    `cond`: a `prompt_parser.MulticondLearnedConditioning` (AND-composed, weighted, step-scheduled prompts — what
+    `p.setup_conds()` leaves in `p.c`) or, already reconstructed, one cond per image as a tensor [B,T,C] / SDXL dict
+    {"crossattn": [B,T,C], "vector": [B,2816]}. `uncond`: list of prompt schedules or a tensor / dict likewise.
+    InstructPix2Pix ("edit") checkpoints and inpainting `image_cond` are outside the accelerated path."""
 
     def __init__(self, sampler):
         self.sampler = sampler
@@ -143,9 +179,14 @@ class CFGDenoiser:
         self.p = None
         self.mask_before_denoising = False
         self.cond_scale_miltiplier = 1.0
-        self._src = {}
-        self.on_cfg_denoiser = []   # callables(x_in, sigma_in, cond_in) -> None   (script_callbacks.on_cfg_denoiser)
-        self.on_cfg_denoised = []   # callables(x_out)                              (on_cfg_denoised)
+        self.padded_cond_uncond = False
+        self.padded_cond_uncond_v0 = False
+        self.need_last_noise_uncond = False
+        self.last_noise_uncond = None
+        self.opts = CFGDenoiserOptions()
+        self._dev_cache = {}
+        self.on_cfg_denoiser = []   # callables(x, sigma_in, cond_in) -> None       (script_callbacks.on_cfg_denoiser)
+        self.on_cfg_denoised = []   # callables(eps)                                (on_cfg_denoised)
         self.on_cfg_after_cfg = []  # callables(denoised) -> denoised | None        (on_cfg_after_cfg)
 
     @property
@@ -155,7 +196,7 @@ class CFGDenoiser:
         return self.model_wrap
 
     def combine_denoised(self, x_out, conds_list, uncond, cond_scale):
-        """sd_samplers_cfg_denoiser.py:74-82 (general form, torch ops)."""
+        """sd_samplers_cfg_denoiser.py:74-82 (torch form; the hot path runs the same arithmetic in sdxe_cfg_combine*)."""
         denoised_uncond = x_out[-uncond.shape[0]:]
         denoised = torch.clone(denoised_uncond)
         for i, conds in enumerate(conds_list):
@@ -163,58 +204,156 @@ class CFGDenoiser:
                 denoised[i] += (x_out[cond_index] - denoised_uncond[i]) * (weight * cond_scale)
         return denoised
 
+    def pad_cond_uncond(self, cond, uncond):
+        """:100-111 — pad the shorter of cond / uncond with empty-prompt chunks (`sd_model.cond_stage_model_empty_prompt`)."""
+        empty = getattr(self.sampler.sd_model, "cond_stage_model_empty_prompt", None)
+        if empty is None:
+            raise L.SdxeError("pad_cond_uncond needs sd_model.cond_stage_model_empty_prompt (the empty prompt's embedding)")
+        num_repeats = (cond.shape[1] - uncond.shape[1]) // empty.shape[1]
+        if num_repeats < 0:
+            cond = pad_cond(cond, -num_repeats, empty)
+            self.padded_cond_uncond = True
+        elif num_repeats > 0:
+            uncond = pad_cond(uncond, num_repeats, empty)
+            self.padded_cond_uncond = True
+        return cond, uncond
+
+    def pad_cond_uncond_v0(self, cond, uncond):
+        """:113-154 — pre-1.6.0 behaviour: repeat uncond's last token vector / truncate it to cond's token count."""
+        is_dict = isinstance(uncond, dict)
+        u = uncond["crossattn"] if is_dict else uncond
+        if u.shape[1] < cond.shape[1]:
+            u = torch.hstack([u, u[:, -1:].repeat([1, cond.shape[1] - u.shape[1], 1])])
+            self.padded_cond_uncond_v0 = True
+        elif u.shape[1] > cond.shape[1]:
+            u = u[:, :cond.shape[1]]
+            self.padded_cond_uncond_v0 = True
+        if is_dict:
+            uncond["crossattn"] = u
+        else:
+            uncond = u
+        return cond, uncond
+
     def _apply_blend(self, latent):
         return latent * self.nmask + self.init_latent * self.mask
+
+    def _dev(self, key, build):
+        t = self._dev_cache.get(key)
+        if t is None:
+            if len(self._dev_cache) > 64:
+                self._dev_cache.clear()
+            t = self._dev_cache[key] = build()
+        return t
+
+    def _run_unet(self, x_in, t, cond_in):
+        sd = self.sampler.sd_model
+        ctx = _cond_tensor(cond_in)
+        vec = cond_in.get("vector") if isinstance(cond_in, dict) else None
+        return sd.apply_model_scaled(x_in, t, ctx, vec)  # engine UNet through the SdUnet seam
 
     def forward(self, x, sigma, uncond, cond, cond_scale, s_min_uncond, image_cond):
         if state.interrupted or state.skipped:
             raise InterruptedException
+        from . import prompt_parser
+
         model = self.inner_model
         sd = self.sampler.sd_model
         lib = L.load()
+        opts = self.opts
+        # ---- per-step conditioning (:168-169)
+        if isinstance(cond, prompt_parser.MulticondLearnedConditioning):
+            conds_list, tensor = prompt_parser.reconstruct_multicond_batch(cond, self.step)
+        else:
+            tensor = cond
+            conds_list = [[(i, 1.0)] for i in range(_cond_tensor(cond).shape[0])]
+        if isinstance(uncond, (list, tuple)):
+            uncond = prompt_parser.reconstruct_cond_batch(uncond, self.step)
         if self.mask_before_denoising and self.mask is not None:
             x = self._apply_blend(x)
-        B = x.shape[0]
-        c_t, u_t = _cond_tensor(cond), _cond_tensor(uncond)
-        if c_t.shape[0] != B or u_t.shape[0] != B:
-            raise L.SdxeError("CFGDenoiser: one cond and one uncond per image expected (AND-composition is not accelerated)")
-        skip_uncond = bool((self.step % 2) and s_min_uncond > 0 and float(sigma[0]) < s_min_uncond)
-        if c_t.shape[1] != u_t.shape[1] and not skip_uncond:
-            raise L.SdxeError("CFGDenoiser: cond / uncond token counts differ; enable pad_cond_uncond upstream")
+        batch_size = len(conds_list)
+        if x.shape[0] != batch_size or _cond_tensor(uncond).shape[0] != batch_size:
+            raise L.SdxeError(f"CFGDenoiser: {x.shape[0]} latents, {batch_size} conds, {_cond_tensor(uncond).shape[0]} unconds")
+        repeats = [len(c) for c in conds_list]
+        n_cond = sum(repeats)
         x = x.float().contiguous()
         sigma = sigma.float().contiguous()
-        rows = B if skip_uncond else 2 * B
-        src = self._src.get((rows, B))
-        if src is None:
-            src = (torch.arange(rows, device=x.device, dtype=torch.int32) % B).contiguous()
-            self._src[(rows, B)] = src
-        sigma_in = sigma if skip_uncond else torch.cat([sigma, sigma])
-        cond_in = c_t if skip_uncond else torch.cat([c_t, u_t])
-        vec_in = None
-        if isinstance(cond, dict) and "vector" in cond:
-            vec_in = cond["vector"] if skip_uncond else torch.cat([cond["vector"], uncond["vector"]])
+        # ---- uncond skipping (:213-227)
+        skip_uncond = False
+        if opts.skip_early_cond != 0.0 and self.step / max(1, self.total_steps or 1) <= opts.skip_early_cond:
+            skip_uncond = True
+        elif (self.step % 2 or opts.s_min_uncond_all) and s_min_uncond > 0 and float(sigma[0]) < s_min_uncond:
+            skip_uncond = True
+        rows = n_cond if skip_uncond else n_cond + batch_size
+        key = (tuple(repeats), skip_uncond)
+        src = self._dev(("src",) + key, lambda: torch.tensor(
+            [i for i, n in enumerate(repeats) for _ in range(n)] + ([] if skip_uncond else list(range(batch_size))),
+            device=x.device, dtype=torch.int32))
+        plain = n_cond == batch_size  # one cond per image: rows [0,B) cond, [B,2B) uncond
+        sigma_in = (sigma if skip_uncond else torch.cat([sigma, sigma])) if plain else sigma[src.long()]
         for cb in self.on_cfg_denoiser:
-            cb(x, sigma_in, cond_in)
-        # --- fused: x_in[r] = x[src[r]] * c_in[r] in the UNet's dtype (cfg_denoiser.py:203 + CompVisDenoiser c_in +
-        #     the dtype cast of sd_hijack_unet.py:43-50)
+            cb(x, sigma_in, tensor)
+        # ---- token-count reconciliation (:229-234)
+        self.padded_cond_uncond = False
+        self.padded_cond_uncond_v0 = False
+        if opts.pad_cond_uncond_v0 and tensor.shape[1] != uncond.shape[1]:
+            tensor, uncond = self.pad_cond_uncond_v0(tensor, uncond)
+        elif opts.pad_cond_uncond and tensor.shape[1] != uncond.shape[1]:
+            tensor, uncond = self.pad_cond_uncond(tensor, uncond)
+        # ---- fused: x_in[r] = x[src[r]] * c_in[r] in the UNet's dtype (:203 + CompVisDenoiser c_in + the dtype cast of
+        #      sd_hijack_unet.py:43-50)
         c_out, c_in = model.get_scalings(sigma_in)
         t = model.sigma_to_t(sigma_in)
         elems = x[0].numel()
         x_in = torch.empty((rows,) + tuple(x.shape[1:]), dtype=sd.dtype_unet, device=x.device)
         stream = L.current_stream()
-        L.check(lib.sdxe_denoiser_in(L.ptr(x), L.ptr(src), L.ptr(c_in.contiguous()), L.ptr(x_in), rows, elems,
+        L.check(lib.sdxe_denoiser_in(L.ptr(x), L.ptr(src), L.ptr(c_in), L.ptr(x_in), rows, elems,
                                      L.torch_dtype_code(sd.dtype_unet), stream), "sdxe_denoiser_in")
-        eps = sd.apply_model_scaled(x_in, t, cond_in, vec_in)  # engine UNet through the SdUnet seam
+        # ---- UNet call(s) (:236-267)
+        if _cond_tensor(tensor).shape[1] == _cond_tensor(uncond).shape[1] or skip_uncond:
+            cond_in = tensor if skip_uncond else catenate_conds([tensor, uncond])
+            if opts.batch_cond_uncond:
+                eps = self._run_unet(x_in, t, cond_in)
+            else:
+                eps = torch.empty_like(x_in)
+                for a in range(0, rows, batch_size):
+                    b = min(a + batch_size, rows)
+                    eps[a:b] = self._run_unet(x_in[a:b], t[a:b], subscript_cond(cond_in, a, b))
+        else:  # cond / uncond token counts differ: they cannot share a batch
+            eps = torch.empty_like(x_in)
+            sub = batch_size * 2 if opts.batch_cond_uncond else batch_size
+            for a in range(0, n_cond, sub):
+                b = min(a + sub, n_cond)
+                eps[a:b] = self._run_unet(x_in[a:b], t[a:b], subscript_cond(tensor, a, b))
+            eps[n_cond:] = self._run_unet(x_in[n_cond:], t[n_cond:], uncond)
         for cb in self.on_cfg_denoised:
             cb(eps)
+        if self.need_last_noise_uncond and not skip_uncond:
+            self.last_noise_uncond = x + eps[n_cond:].float() * c_out[n_cond:].view(-1, 1, 1, 1)
+        # ---- x_out = x_in + eps * c_out and the CFG combine, fused (:272-289)
         scale = 1.0 if skip_uncond else float(cond_scale) * self.cond_scale_miltiplier
         denoised = torch.empty_like(x)
-        if skip_uncond:
-            # denoised = x + eps * c_out (no uncond branch evaluated: cfg_denoiser.py:229-231,272-275)
-            denoised = x + eps.float() * c_out.view(-1, 1, 1, 1)
-        else:
-            L.check(lib.sdxe_cfg_combine(L.ptr(x), L.ptr(eps), L.ptr(sigma), scale, L.ptr(denoised), B, elems,
+        if plain and not skip_uncond and all(c[0][1] == 1.0 for c in conds_list):
+            L.check(lib.sdxe_cfg_combine(L.ptr(x), L.ptr(eps), L.ptr(sigma), scale, L.ptr(denoised), batch_size, elems,
                                          L.torch_dtype_code(eps.dtype), stream), "sdxe_cfg_combine")
+        else:
+            wkey = ("csr",) + key + (tuple(w for c in conds_list for _, w in c), scale)
+
+            def build():
+                ptr, k = [0], 0
+                for n in repeats:
+                    k += n
+                    ptr.append(k)
+                # skipped uncond: the reference puts each image's FIRST cond result where the uncond result would be
+                urows = [c[0][0] for c in conds_list] if skip_uncond else [n_cond + i for i in range(batch_size)]
+                return (torch.tensor(ptr, device=x.device, dtype=torch.int32),
+                        torch.tensor([j for c in conds_list for j, _ in c], device=x.device, dtype=torch.int32),
+                        torch.tensor([w * scale for c in conds_list for _, w in c], device=x.device, dtype=torch.float32),
+                        torch.tensor(urows, device=x.device, dtype=torch.int32))
+
+            row_ptr, cond_rows, cond_w, uncond_rows = self._dev(wkey, build)
+            L.check(lib.sdxe_cfg_combine_multi(L.ptr(x), L.ptr(eps), L.ptr(sigma), L.ptr(row_ptr), L.ptr(cond_rows), L.ptr(cond_w),
+                                               L.ptr(uncond_rows), L.ptr(denoised), batch_size, elems,
+                                               L.torch_dtype_code(eps.dtype), stream), "sdxe_cfg_combine_multi")
         if not self.mask_before_denoising and self.mask is not None:
             denoised = self._apply_blend(denoised)
         self.sampler.last_latent = denoised

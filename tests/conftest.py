@@ -19,3 +19,14 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _strict_fp32_oracle():
+    """The fp32 oracle must be fp32: PyTorch lets cuDNN convolutions run in TF32 (10-bit mantissa) by default, which
+    would put fp16-sized noise into the "ground truth" every parity number is measured against."""
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
