@@ -326,7 +326,6 @@ int attention_init() {
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (attention2_init() != 0) return -1;
     if (attentionx_init() != 0) return -1;
-    if (attention4_init() != 0) return -1;
     done = true;
   }
   return 0;
@@ -335,15 +334,13 @@ int attention_init() {
 int attention_launch(const AttnArgs& a_in, bool bf16, cudaStream_t stream) {
   AttnArgs a = a_in;
   {
-    // SDXE_ATTN: 2 = attention2 (two Q tiles, 16 softmax warps) where eligible [default],
-    //            4 = attention4 (two Q tiles, one softmax thread per row, early S release; measured equal within noise),
+    // SDXE_ATTN: 2 = attention2 (two Q tiles, an MMA issuer per tile, 16 softmax warps) where eligible [default],
     //            1 = this file's kernel only
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("SDXE_ATTN"); mode = e ? atoi(e) : 2; }
     static int usex = -1;  // SDXE_ATTNX=0: keep short-KV (cross-) attention on the general kernels
     if (usex < 0) { const char* e = getenv("SDXE_ATTNX"); usex = e ? atoi(e) : 1; }
     if (usex && attentionx_eligible(a)) return attentionx_launch(a, bf16, stream);
-    if (mode == 4 && attention4_eligible(a)) return attention4_launch(a, bf16, stream);
     if (mode >= 2 && attention2_eligible(a)) return attention2_launch(a, bf16, stream);
   }
   if (a.dv_slabs < 1 || a.dv_slabs > 4 || a.dqk_slabs < 1 || a.dqk_slabs > 8 || a.dv % 8 != 0 || a.dv > a.dv_slabs * 64) {

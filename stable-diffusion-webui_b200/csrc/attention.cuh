@@ -21,8 +21,7 @@ struct alignas(64) AttnArgs {
   void* out;        // [B*Nq, ldo] 16-bit; head h writes columns out_col0 + h*dv ...
   int ldo;
   int out_col0;
-  int dbg;          // knockout experiments (SDXE_ATT_KO), 0 in production
-  unsigned long long* trace;  // timeline of CTA (0,0) (SDXE_ATT_TRACE), null in production
+  unsigned long long* trace;  // timeline of CTA (0,0), only in builds with -DSDXE_ATT_TRACE=1; null otherwise
 };
 
 int attention_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
@@ -35,9 +34,5 @@ int attention2_init();
 bool attentionx_eligible(const AttnArgs& a);
 int attentionx_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
 int attentionx_init();
-// two Q tiles, one softmax thread per query row, S handed back to the MMA warp right after the register copy (attention4.cu)
-bool attention4_eligible(const AttnArgs& a);
-int attention4_launch(const AttnArgs& a, bool bf16, cudaStream_t stream);
-int attention4_init();
 
 }  // namespace sdxe

@@ -228,6 +228,16 @@ SDXE_DEVINL void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from tensor memory (TS form): A = [128 rows (lanes) x 16 k] 16-bit, two elements per 32-bit
+// column (k even in the low half), 8 columns per K = 16 step
+SDXE_DEVINL void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 SDXE_DEVINL void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 SDXE_DEVINL void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -333,6 +343,20 @@ SDXE_DEVINL float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA pipe (Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, r = x - n in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^r, 2^n through the exponent field). Max relative error 7.5e-5 — below half an ulp of fp16
+// (2.4e-4) and far below bf16's (2e-3): used for a fraction of the softmax exponentials so that the MUFU pipe
+// (16 ex2 / clk / SM) is not the only unit doing them (the FA-4 trick). x <= ~100; x -> -inf gives 2^-125 (~0).
+SDXE_DEVINL float ex2_poly3(float x) {
+  x = fmaxf(x, -125.f);
+  const float magic = 12582912.f;
+  const float t = x + magic;
+  const float r = x - (t - magic);
+  float p = fmaf(0.0551716685295105f, r, 0.2426111400127411f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 SDXE_DEVINL float rcp_approx(float x) {
   float y;

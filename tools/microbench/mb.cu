@@ -129,6 +129,101 @@ __global__ void acc_kernel(const float* x, float* y3, float* y4, float* ym, int 
   if (i < n) { y3[i] = exp2_poly<3>(x[i]); y4[i] = exp2_poly<4>(x[i]); ym[i] = ex2_approx(x[i]); }
 }
 
+
+// ------------------------------------------------------------------------------------------------ sync primitive costs
+// one warp, clock64 around N repetitions of each primitive (issue + completion latency as seen by the issuing warp)
+__global__ void __launch_bounds__(128, 1) sync_kernel(long long* out) {
+  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ uint32_t tptr;
+  __shared__ __align__(16) uint32_t buf[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tptr), 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp != 0) return;
+  const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]);
+  const int N = 64;
+  long long t0, t1;
+  // complete phase 0 of bar0 so that waits on parity 0 succeed at once
+  if (lane == 0) mbar_arrive(b0);
+  __syncwarp();
+  // (0) try_wait on a completed phase, all 32 lanes
+  t0 = clk();
+  for (int i = 0; i < N; ++i) mbar_wait(b0, 0);
+  t1 = clk();
+  if (lane == 0) out[0] = (t1 - t0) / N;
+  // (1) same, lane 0 only + __syncwarp
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { if (lane == 0) mbar_wait(b0, 0); __syncwarp(); }
+  t1 = clk();
+  if (lane == 0) out[1] = (t1 - t0) / N;
+  // (2) test_wait, all lanes + any_sync
+  t0 = clk();
+  int acc = 0;
+  for (int i = 0; i < N; ++i) acc += __any_sync(0xffffffffu, mbar_test(b0, 0));
+  t1 = clk();
+  if (lane == 0) out[2] = (t1 - t0) / N + (acc == 12345);
+  // (3) tcgen05.commit (no MMA outstanding), elected lane, then wait for the arrival (round trip)
+  t0 = clk();
+  for (int i = 0; i < N; ++i) {
+    if (elect_one()) tc_commit(b1);
+    __syncwarp();
+    mbar_wait(b1, (uint32_t)(i & 1));
+  }
+  t1 = clk();
+  if (lane == 0) out[3] = (t1 - t0) / N;
+  // (4) tcgen05.commit issue only (arrivals drain in the background; phases flip freely)
+  t0 = clk();
+  for (int i = 0; i < N; ++i) {
+    if (elect_one()) tc_commit(b1);
+    __syncwarp();
+  }
+  t1 = clk();
+  if (lane == 0) out[4] = (t1 - t0) / N;
+  // (5) mbarrier.arrive by lane 0
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { if (lane == 0) mbar_arrive(smem_u32(&bars[2])); __syncwarp(); }
+  t1 = clk();
+  if (lane == 0) out[5] = (t1 - t0) / N;
+  // (6) fence.proxy.async after a shared store
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { buf[lane] = i; fence_proxy_async_smem(); }
+  t1 = clk();
+  if (lane == 0) out[6] = (t1 - t0) / N;
+  // (7) tcgen05 fence before + after
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { tc_fence_before(); tc_fence_after(); }
+  t1 = clk();
+  if (lane == 0) out[7] = (t1 - t0) / N;
+  // (8) elect_one + syncwarp alone
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { if (elect_one()) buf[0] = i; __syncwarp(); }
+  t1 = clk();
+  if (lane == 0) out[8] = (t1 - t0) / N;
+  // (9) bar.sync of 64 threads is measured elsewhere; here: st.shared.v4 x8 per lane (the P row) 
+  t0 = clk();
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_u32(&buf[0]) + (uint32_t)(((lane + c) & 15) * 16)), "r"(i) : "memory");
+  }
+  t1 = clk();
+  if (lane == 0) out[9] = (t1 - t0) / N;
+  // (10) clock64 read + global store (the trace stamp itself)
+  t0 = clk();
+  for (int i = 0; i < N; ++i) { if (lane == 0) out[16 + (i & 7)] = clk(); }
+  t1 = clk();
+  if (lane == 0) out[10] = (t1 - t0) / N;
+  __syncwarp();
+  tc_fence_before();
+  tmem_dealloc(tptr, 32);
+}
+
 template <typename K, typename... A>
 static double run(K kern, int threads, int iters, A... args) {
   long long* d;
@@ -149,6 +244,21 @@ static double run(K kern, int threads, int iters, A... args) {
 int main() {
   uint32_t* sink;
   CK(cudaMalloc(&sink, 64));
+  {
+    long long* d;
+    CK(cudaMalloc(&d, 64 * sizeof(long long)));
+    sync_kernel<<<1, 128>>>(d);
+    CK(cudaDeviceSynchronize());
+    sync_kernel<<<1, 128>>>(d);
+    CK(cudaDeviceSynchronize());
+    long long h[16];
+    CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    const char* nm[11] = {"mbarrier.try_wait (done phase), 32 lanes", "mbarrier.try_wait (done phase), lane 0 + syncwarp", "mbarrier.test_wait + any_sync, 32 lanes",
+                          "tcgen05.commit -> arrival seen (round trip)", "tcgen05.commit issue only", "mbarrier.arrive lane 0 + syncwarp",
+                          "st.shared + fence.proxy.async", "tcgen05.fence before+after", "elect_one + st.shared + syncwarp", "2 x st.shared.v4", "clock64 + st.global (trace stamp)"};
+    printf("== sync primitive costs (clk per operation, one warp)\n");
+    for (int i = 0; i < 11; ++i) printf("  %-52s %lld\n", nm[i], h[i]);
+  }
   const int iters = 2000;
   printf("== tcgen05.ld 32x32b.x32 (4096 B per warp-instruction), grid 148 x 1 CTA/SM\n");
   for (int warps : {4, 8, 16}) {
