@@ -98,6 +98,15 @@ int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int 
  * Engine kind SDXE_MODEL_VAE_ENCODER, weights "encoder.*" and "quant_conv.*". H, W multiples of 2^(num_levels-1) (8). */
 int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int w, int io_dtype, void* stream);
 
+/* Execution-plan cache. A plan (buffers from the engine's pool, tensor maps, one CUDA graph) is built per input shape
+ * (n, h, w, ctx_len) on first use and replayed afterwards; at most `max_plans` (default 8) are kept, least recently used
+ * evicted, and after an eviction free pool memory beyond `pool_limit_mb` (default 6144; < 0 = keep) returns to the
+ * driver. An allocation failure during a plan build drops every cached plan and retries once; if that fails the call
+ * returns -1 ("out of device memory ...") with nothing leaked. All calls on one engine must use one stream at a time. */
+int sdxe_set_plan_cache(sdxe_engine* e, int max_plans, int64_t pool_limit_mb);
+/* bytes held by the engine's activation pool (cached plans + free list); *n_plans = cached plans. */
+int64_t sdxe_pool_bytes(sdxe_engine* e, int64_t* n_plans);
+
 /* Per-kernel-class timing: while enabled, forward / decode calls run their plan eagerly with a CUDA event pair
  * around every launch on the launching stream. kind: 0 GEMM (tcgen05), 1 conv3x3 implicit GEMM (tcgen05),
  * 2 attention, 3 GroupNorm, 4 LayerNorm, 5 other. flops / bytes are ALGORITHMIC totals of the timed launches. */

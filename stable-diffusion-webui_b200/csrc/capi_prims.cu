@@ -69,15 +69,15 @@ int sdxe_gemm(const void* A, const void* W, void* out, int M, int N, int K, cons
   if (geglu) {
     // interleave value / gate rows per tile so that both land in the same accumulator tile
     SDXE_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)N * K * 2 + (size_t)N * 4, stream));
-    if (pack_weight_launch(W, dtype, scratch, PACK_GEGLU, N, K, K, a.BN, bf16, stream)) return -1;
+    if (pack_weight_launch(W, dtype, scratch, PACK_GEGLU, N, K, K, a.BN, bf16, stream)) { cudaFreeAsync(scratch, stream); return -1; }
     Wp = scratch;
     if (bias) {
       float* b2 = (float*)((char*)scratch + (size_t)N * K * 2);
-      if (pack_vector_launch(bias, SDXE_F32, b2, N, a.BN, false, bf16, stream)) return -1;
+      if (pack_vector_launch(bias, SDXE_F32, b2, N, a.BN, false, bf16, stream)) { cudaFreeAsync(scratch, stream); return -1; }
       bp = b2;
     }
   }
-  if (make_tmap_2d(&a.tmA, A, M, K, K, 128)) return -1;
+  if (make_tmap_2d(&a.tmA, A, M, K, K, 128)) { if (scratch) cudaFreeAsync(scratch, stream); return -1; }
   a.tmA2 = a.tmA;
   a.bias = bp;
   a.residual = residual;
@@ -85,7 +85,7 @@ int sdxe_gemm(const void* A, const void* W, void* out, int M, int N, int K, cons
   a.out = out;
   a.ldo = geglu ? N / 2 : N;
   a.rows_per_sample = 1;
-  if (gemm_finish_args(a, Wp, N, K)) return -1;
+  if (gemm_finish_args(a, Wp, N, K)) { if (scratch) cudaFreeAsync(scratch, stream); return -1; }
   int rc = gemm_launch(a, bf16, stream);
   count_launch();
   if (scratch) cudaFreeAsync(scratch, stream);

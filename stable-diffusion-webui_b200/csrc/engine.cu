@@ -157,7 +157,17 @@ struct sdxe_engine {
   // activation pool
   std::multimap<size_t, void*> free_list;
   std::vector<void*> all_allocs;
+  // Plan cache: one static plan (buffers + tensor maps + CUDA graph) per input shape, least-recently-used eviction.
+  // A long-lived webui process sees many shapes (resolutions, batch sizes, 77 / 154 / 231-token prompts, B vs 2B
+  // batches under s_min_uncond); every plan pins its own buffers (SDXL: > 100 MB of cross-attention k|v alone), so an
+  // unbounded cache grows until cudaMalloc fails.
   std::map<std::string, std::unique_ptr<Plan>> plans;
+  int max_plans = 8;                    // SDXE_MAX_PLANS
+  size_t pool_limit = (size_t)6 << 30;  // SDXE_POOL_LIMIT_MB: free (unowned) pool bytes kept after an eviction
+  uint64_t tick = 0;
+  std::vector<Buf>* track = nullptr;    // while a plan is being built: the buffers it currently holds
+  std::vector<void*>* touched = nullptr;  // ... and every pool block it used at any point (scratch it released again)
+  bool alloc_failed = false;
   cudaStream_t cap_stream = nullptr;
   bool use_graph = true;
   bool profiling = false;
@@ -206,6 +216,9 @@ struct Plan {
   std::vector<OpRec> pre, body, post;
   cudaGraphExec_t gexec = nullptr;
   cudaGraph_t graph = nullptr;
+  std::vector<Buf> owned;   // buffers still held when the build finished: returned to the pool on eviction
+  std::vector<void*> used;  // every pool block the plan's kernels touch (owned + scratch shared through the free list)
+  uint64_t last_use = 0;
   // per-call caller pointers, read by pre / post ops
   const void *x = nullptr, *t = nullptr, *ctx = nullptr, *y = nullptr;
   void* out = nullptr;
@@ -891,19 +904,34 @@ int sdxe_engine::build_vae_encoder() {
 // =================================================================================================================
 Buf sdxe_engine::alloc(size_t bytes) {
   bytes = align_up(std::max<size_t>(bytes, 256), 1024);
+  Buf b;
   auto it = free_list.lower_bound(bytes);
   if (it != free_list.end() && it->first <= bytes + bytes / 2 + (1 << 20)) {
-    Buf b{it->second, it->first};
+    b = Buf{it->second, it->first};
     free_list.erase(it);
-    return b;
+  } else {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();  // clear the sticky error; the plan build is abandoned by its caller (alloc_failed)
+      set_last_error(__FILE__, __LINE__, "cudaMalloc failed (activation pool)");
+      alloc_failed = true;
+      return Buf();
+    }
+    all_allocs.push_back(p);
+    b = Buf{p, bytes};
   }
-  void* p = nullptr;
-  if (cudaMalloc(&p, bytes) != cudaSuccess) { set_last_error(__FILE__, __LINE__, "cudaMalloc failed (activation pool)"); return Buf(); }
-  all_allocs.push_back(p);
-  return Buf{p, bytes};
+  if (track) track->push_back(b);
+  if (touched) touched->push_back(b.p);
+  return b;
 }
 void sdxe_engine::release(Buf& b) {
-  if (b.p) free_list.insert({b.bytes, b.p});
+  if (b.p) {
+    free_list.insert({b.bytes, b.p});
+    if (track) {
+      for (size_t i = track->size(); i-- > 0;)
+        if ((*track)[i].p == b.p) { track->erase(track->begin() + i); break; }
+    }
+  }
   b.p = nullptr;
 }
 // =================================================================================================================
@@ -1306,6 +1334,85 @@ int build_vae_plan(sdxe_engine* e, Plan* p, int n, int h, int w) {
 // =================================================================================================================
 // C-ABI
 // =================================================================================================================
+namespace {
+
+// Drop the least recently used plan: its graph is destroyed and the buffers it pinned go back to the pool; pool memory
+// beyond pool_limit is returned to the driver (largest blocks first).
+void evict_lru(sdxe_engine* e) {
+  auto victim = e->plans.end();
+  for (auto it = e->plans.begin(); it != e->plans.end(); ++it)
+    if (victim == e->plans.end() || it->second->last_use < victim->second->last_use) victim = it;
+  if (victim == e->plans.end()) return;
+  cudaDeviceSynchronize();  // the plan's last replay may still be running
+  for (auto& b : victim->second->owned)
+    if (b.p) e->free_list.insert({b.bytes, b.p});
+  e->plans.erase(victim);
+  // free-list blocks double as scratch of the plans that are still cached: only blocks no live plan touches may go
+  size_t free_bytes = 0;
+  for (auto& kv : e->free_list) free_bytes += kv.first;
+  if (free_bytes <= e->pool_limit) return;
+  std::vector<void*> live;
+  for (auto& kv : e->plans) live.insert(live.end(), kv.second->used.begin(), kv.second->used.end());
+  std::sort(live.begin(), live.end());
+  for (auto it = e->free_list.end(); it != e->free_list.begin() && free_bytes > e->pool_limit;) {
+    --it;
+    if (std::binary_search(live.begin(), live.end(), it->second)) continue;
+    free_bytes -= it->first;
+    cudaFree(it->second);
+    e->all_allocs.erase(std::remove(e->all_allocs.begin(), e->all_allocs.end(), it->second), e->all_allocs.end());
+    it = e->free_list.erase(it);
+  }
+}
+
+template <class BuildFn>
+Plan* get_plan(sdxe_engine* e, const std::string& key, BuildFn build) {
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) {
+    it->second->last_use = ++e->tick;
+    return it->second.get();
+  }
+  static const int env_max = [] { const char* v = getenv("SDXE_MAX_PLANS"); return v ? std::max(1, atoi(v)) : 0; }();
+  static const long env_pool = [] { const char* v = getenv("SDXE_POOL_LIMIT_MB"); return v ? std::max(0l, atol(v)) : -1l; }();
+  if (env_max) e->max_plans = env_max;  // the environment overrides sdxe_set_plan_cache (debugging aid)
+  if (env_pool >= 0) e->pool_limit = (size_t)env_pool << 20;
+  while ((int)e->plans.size() >= e->max_plans) evict_lru(e);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    std::unique_ptr<Plan> p(new Plan());
+    p->e = e;
+    std::vector<Buf> held;
+    std::vector<void*> used;
+    e->track = &held;
+    e->touched = &used;
+    e->alloc_failed = false;
+    const int rc = build(p.get());
+    e->track = nullptr;
+    e->touched = nullptr;
+    if (rc == 0 && !e->alloc_failed) {
+      std::sort(used.begin(), used.end());
+      used.erase(std::unique(used.begin(), used.end()), used.end());
+      p->used = std::move(used);
+      p->owned = std::move(held);
+      p->last_use = ++e->tick;
+      return e->plans.emplace(key, std::move(p)).first->second.get();
+    }
+    for (auto& b : held)  // a failed build leaks nothing: whatever it still held goes back to the pool
+      if (b.p) e->free_list.insert({b.bytes, b.p});
+    if (!e->alloc_failed || attempt == 1) break;
+    // out of device memory: drop every cached plan and the whole free pool, then try once more
+    while (!e->plans.empty()) evict_lru(e);
+    cudaDeviceSynchronize();
+    for (auto& kv : e->free_list) {
+      cudaFree(kv.second);
+      e->all_allocs.erase(std::remove(e->all_allocs.begin(), e->all_allocs.end(), kv.second), e->all_allocs.end());
+    }
+    e->free_list.clear();
+  }
+  if (e->alloc_failed) set_last_error(__FILE__, __LINE__, "out of device memory while building the execution plan");
+  return nullptr;
+}
+
+}  // namespace
+
 extern "C" {
 
 int sdxe_create(const sdxe_config* cfg, sdxe_engine** out) {
@@ -1404,16 +1511,28 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
   if (!x || !t || !ctx || !out || n <= 0 || h <= 0 || w <= 0 || ctx_len <= 0) EFAIL("sdxe_unet_forward: bad argument");
   if (io_dtype != SDXE_F16 && io_dtype != SDXE_BF16 && io_dtype != SDXE_F32) EFAIL("sdxe_unet_forward: io dtype");
   const std::string key = "u:" + std::to_string(n) + ":" + std::to_string(h) + ":" + std::to_string(w) + ":" + std::to_string(ctx_len);
-  auto it = e->plans.find(key);
-  if (it == e->plans.end()) {
-    std::unique_ptr<Plan> p(new Plan());
-    p->e = e;
-    if (build_unet_plan(e, p.get(), n, h, w, ctx_len) != 0) return -1;
-    it = e->plans.emplace(key, std::move(p)).first;
-  }
-  Plan* p = it->second.get();
+  Plan* p = get_plan(e, key, [&](Plan* pl) { return build_unet_plan(e, pl, n, h, w, ctx_len); });
+  if (!p) return -1;
   p->x = x; p->t = t; p->ctx = ctx; p->y = y; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
+}
+
+int sdxe_set_plan_cache(sdxe_engine* e, int max_plans, int64_t pool_limit_mb) {
+  if (!e || max_plans < 1) EFAIL("sdxe_set_plan_cache: bad argument");
+  e->max_plans = max_plans;
+  if (pool_limit_mb >= 0) e->pool_limit = (size_t)pool_limit_mb << 20;
+  while ((int)e->plans.size() > e->max_plans) evict_lru(e);
+  return 0;
+}
+
+int64_t sdxe_pool_bytes(sdxe_engine* e, int64_t* n_plans) {
+  if (!e) return -1;
+  if (n_plans) *n_plans = (int64_t)e->plans.size();
+  int64_t total = 0;
+  for (auto& kv : e->free_list) total += (int64_t)kv.first;
+  for (auto& kv : e->plans)
+    for (auto& b : kv.second->owned) total += (int64_t)b.bytes;
+  return total;
 }
 
 int sdxe_profile(sdxe_engine* e, int enable) {
@@ -1436,14 +1555,8 @@ int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int 
   if (!z || !out || n <= 0 || h <= 0 || w <= 0) EFAIL("sdxe_vae_decode: bad argument");
   if (io_dtype != SDXE_F16 && io_dtype != SDXE_BF16 && io_dtype != SDXE_F32) EFAIL("sdxe_vae_decode: io dtype");
   const std::string key = "v:" + std::to_string(n) + ":" + std::to_string(h) + ":" + std::to_string(w);
-  auto it = e->plans.find(key);
-  if (it == e->plans.end()) {
-    std::unique_ptr<Plan> p(new Plan());
-    p->e = e;
-    if (build_vae_plan(e, p.get(), n, h, w) != 0) return -1;
-    it = e->plans.emplace(key, std::move(p)).first;
-  }
-  Plan* p = it->second.get();
+  Plan* p = get_plan(e, key, [&](Plan* pl) { return build_vae_plan(e, pl, n, h, w); });
+  if (!p) return -1;
   p->x = z; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
 }
@@ -1454,14 +1567,8 @@ int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int 
   if (!x || !out || n <= 0 || h <= 0 || w <= 0 || (h % f) || (w % f)) EFAIL("sdxe_vae_encode: bad argument (H, W must be multiples of the encoder's downsampling factor)");
   if (io_dtype != SDXE_F16 && io_dtype != SDXE_BF16 && io_dtype != SDXE_F32) EFAIL("sdxe_vae_encode: io dtype");
   const std::string key = "e:" + std::to_string(n) + ":" + std::to_string(h) + ":" + std::to_string(w);
-  auto it = e->plans.find(key);
-  if (it == e->plans.end()) {
-    std::unique_ptr<Plan> p(new Plan());
-    p->e = e;
-    if (build_vae_encode_plan(e, p.get(), n, h, w) != 0) return -1;
-    it = e->plans.emplace(key, std::move(p)).first;
-  }
-  Plan* p = it->second.get();
+  Plan* p = get_plan(e, key, [&](Plan* pl) { return build_vae_encode_plan(e, pl, n, h, w); });
+  if (!p) return -1;
   p->x = x; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
 }

@@ -63,6 +63,33 @@ class VAESpec:
         return VAESpec(**{k: (list(getattr(cfg, k)) if isinstance(getattr(cfg, k), (list, tuple)) else getattr(cfg, k))
                           for k in VAESpec.__dataclass_fields__})
 
+    @staticmethod
+    def from_state_dict(sd) -> "VAESpec":
+        """ddconfig read back from a `first_stage_model` state dict (decoder.* and / or encoder.* keys): the KL-f8 VAE of
+        SD1.x / SDXL gives the defaults; anything the engine does not implement (attention outside the mid block, a
+        z_channels != embed_dim pairing it cannot pack, ...) raises SdxeError so that callers keep the stock VAE."""
+        side = "decoder" if any(k.startswith("decoder.") for k in sd) else "encoder"
+        if f"{side}.conv_in.weight" not in sd:
+            raise L.SdxeError("not an AutoencoderKL state dict (no conv_in)")
+        levels = sorted({int(k.split(".")[2]) for k in sd if k.startswith(f"{side}.{'up' if side == 'decoder' else 'down'}.")})
+        if not levels or levels != list(range(len(levels))):
+            raise L.SdxeError("unrecognised VAE level layout")
+        if any(".attn." in k and not k.startswith(f"{side}.mid.") for k in sd if k.startswith(side)):
+            raise L.SdxeError("VAE with attention outside the mid block is not implemented")
+        if side == "decoder":
+            ch = sd["decoder.up.0.block.0.conv1.weight"].shape[0]
+            mult = [sd[f"decoder.up.{l}.block.0.conv1.weight"].shape[0] // ch for l in levels]
+            nres = len({int(k.split(".")[4]) for k in sd if k.startswith("decoder.up.0.block.")}) - 1
+            z = sd["decoder.conv_in.weight"].shape[1]
+            out_ch = sd["decoder.conv_out.weight"].shape[0]
+        else:
+            ch = sd["encoder.conv_in.weight"].shape[0]
+            mult = [sd[f"encoder.down.{l}.block.0.conv1.weight"].shape[0] // ch for l in levels]
+            nres = len({int(k.split(".")[4]) for k in sd if k.startswith("encoder.down.0.block.")})
+            z = sd["encoder.conv_out.weight"].shape[0] // 2
+            out_ch = sd["encoder.conv_in.weight"].shape[1]
+        return VAESpec(ch=int(ch), out_ch=int(out_ch), ch_mult=[int(m) for m in mult], num_res_blocks=int(nres), z_channels=int(z))
+
 
 def _dtype_code(dtype: torch.dtype) -> int:
     if dtype not in (torch.float16, torch.bfloat16):
@@ -130,6 +157,18 @@ class _EngineBase:
 
     def profile(self, enable: bool):
         L.check(self.lib.sdxe_profile(self._h, 1 if enable else 0), "sdxe_profile")
+
+    def set_plan_cache(self, max_plans: int = 8, pool_limit_mb: int = 6144):
+        """Bound the per-shape execution-plan cache (LRU) and the free activation pool kept after an eviction."""
+        L.check(self.lib.sdxe_set_plan_cache(self._h, int(max_plans), int(pool_limit_mb)), "sdxe_set_plan_cache")
+
+    def pool_stats(self):
+        """(bytes held by the activation pool, number of cached plans)."""
+        import ctypes
+
+        n = ctypes.c_int64(0)
+        b = self.lib.sdxe_pool_bytes(self._h, ctypes.byref(n))
+        return int(b), int(n.value)
 
     def profile_read(self) -> dict:
         """{kind: {"ms", "flops", "bytes", "launches"}} accumulated since profile(True)."""

@@ -76,7 +76,7 @@ def save_safetensors(sd: Dict[str, torch.Tensor], path: str, metadata: Optional[
         v = v.detach().cpu().contiguous()
         if v.dtype not in _ST_NAMES:
             raise L.SdxeError(f"cannot store dtype {v.dtype}")
-        raw = v.view(torch.uint8).numpy().tobytes() if v.numel() else b""
+        raw = v.reshape(-1).view(torch.uint8).numpy().tobytes() if v.numel() else b""
         head[k] = {"dtype": _ST_NAMES[v.dtype], "shape": list(v.shape), "data_offsets": [off, off + len(raw)]}
         chunks.append(raw)
         off += len(raw)

@@ -40,9 +40,14 @@ except Exception:  # headless: structural twins of modules/sd_unet.py:63-83
 def guess_unet_spec(state_dict: Dict[str, torch.Tensor]) -> UNetSpec:
     """Architecture from the checkpoint's own keys (the webui guesses from keys too: sd_models_config.py:72-114)."""
     if "label_emb.0.0.weight" in state_dict:
+        w0 = state_dict.get("input_blocks.0.0.weight")
+        wk = state_dict.get("input_blocks.4.1.transformer_blocks.0.attn2.to_k.weight")
+        if w0 is None or w0.shape[1] != 4 or wk is None or wk.shape[1] != 2048 or state_dict["label_emb.0.0.weight"].shape[1] != 2816:
+            raise L.SdxeError("SDXL-like checkpoint the engine does not implement (inpainting / refiner layout)")
         return UNetSpec.sdxl()
     w = state_dict.get("input_blocks.1.1.transformer_blocks.0.attn2.to_k.weight")
-    if w is not None and w.shape[1] == 768 and state_dict["input_blocks.0.0.weight"].shape[0] == 320:
+    w0 = state_dict.get("input_blocks.0.0.weight")
+    if w is not None and w0 is not None and w.shape[1] == 768 and w0.shape[0] == 320 and w0.shape[1] == 4:
         return UNetSpec.sd15()
     raise L.SdxeError("unrecognised UNet checkpoint layout: pass an explicit UNetSpec")
 
@@ -95,11 +100,13 @@ class SdxeUnet(_SdUnetBase):
 
 class SdxeUnetOption(_SdUnetOptionBase):
     def __init__(self, model_name: str, state_dict_provider, spec: Optional[UNetSpec] = None, dtype=torch.float16,
-                 device="cuda:0", prefix: str = ""):
+                 device="cuda:0", prefix: str = "", loras_provider=None):
         self.model_name = model_name          # "Automatic" picks this option when the checkpoint name matches
         self.label = f"[sdxe] {model_name}"
         self._provider = state_dict_provider  # callable -> state dict (read lazily, at create_unet time)
+        self._loras = loras_provider          # callable -> [(lora state dict, unet multiplier)] active at activation time
         self._spec, self._dtype, self._device, self._prefix = spec, dtype, device, prefix
 
     def create_unet(self):
-        return SdxeUnet(self._provider(), self._spec, self._dtype, self._device, self._prefix)
+        loras = self._loras() if self._loras is not None else None
+        return SdxeUnet(self._provider(), self._spec, self._dtype, self._device, self._prefix, loras=loras)

@@ -150,3 +150,37 @@ def test_full_vae_decode(cuda, dtype):
     print(f"full vae {dtype}: engine {e_eng:.3e} ref16 {e_ref:.3e}")
     assert e_eng < max(3 * e_ref, _floor(dtype)), (e_eng, e_ref)
     eng.close()
+
+
+def test_plan_cache_lru_bounds_memory(cuda):
+    """sdxe_set_plan_cache: with room for 2 plans, cycling through 4 input shapes keeps evicting and rebuilding; the
+    outputs stay bit-identical to the first time each shape ran and the pool stops growing after the first cycle."""
+    from oracle.synth import init_module_
+    from oracle.unet import UNetModel, tiny_config
+    from sdwebui_b200.engine import UNetEngine, UNetSpec
+
+    cfg = tiny_config()
+    m = init_module_(UNetModel(cfg), 3).eval()
+    eng = UNetEngine(UNetSpec.from_any(cfg), dtype=torch.float16, device=cuda)
+    eng.load_state_dict({k: v.to(cuda) for k, v in m.state_dict().items()})
+    eng.finalize()
+    eng.set_plan_cache(max_plans=2, pool_limit_mb=0)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    shapes = [(2, 16, 16, 77), (4, 16, 32, 77), (2, 32, 32, 154), (6, 16, 16, 77)]
+    ins, first, sizes = [], [], []
+    for n, h, w, T in shapes:
+        ins.append((torch.randn(n, 4, h, w, device=cuda, generator=g).half(), torch.linspace(900, 10, n, device=cuda).half(),
+                    torch.randn(n, T, cfg.context_dim, device=cuda, generator=g).half()))
+    for cycle in range(3):
+        for i, (x, t, c) in enumerate(ins):
+            out = eng.forward(x, t, c, None)
+            if cycle == 0:
+                first.append(out.clone())
+            else:
+                assert torch.equal(out, first[i]), (cycle, i)
+            assert eng.pool_stats()[1] <= 2
+        torch.cuda.synchronize()
+        sizes.append(eng.pool_stats()[0])
+    print("pool bytes per cycle", sizes)
+    assert sizes[2] <= sizes[1]
+    eng.close()
