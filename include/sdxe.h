@@ -34,7 +34,7 @@ extern "C" {
 /* 16-bit storage / compute input format of activations and weights (accumulation is always fp32). */
 enum sdxe_dtype { SDXE_F16 = 0, SDXE_BF16 = 1, SDXE_F32 = 2 };
 
-enum sdxe_model_kind { SDXE_MODEL_UNET = 0, SDXE_MODEL_VAE_DECODER = 1, SDXE_MODEL_VAE_ENCODER = 2 };
+enum sdxe_model_kind { SDXE_MODEL_UNET = 0, SDXE_MODEL_VAE_DECODER = 1, SDXE_MODEL_VAE_ENCODER = 2, SDXE_MODEL_CLIP_TEXT = 3 };
 
 #define SDXE_MAX_LEVELS 8
 
@@ -61,7 +61,15 @@ typedef struct sdxe_config {
   int32_t vae_ch;               /* 128 */
   int32_t vae_z_channels;       /* 4 */
   int32_t vae_out_ch;           /* 3 */
-  int32_t reserved[8];
+  /* SDXE_MODEL_CLIP_TEXT (transformers CLIPTextModel / open_clip text tower; CLIP-L: 49408, 768, 3072, 12, 12, 77, 0) */
+  int32_t clip_vocab;
+  int32_t clip_hidden;
+  int32_t clip_intermediate;
+  int32_t clip_layers;
+  int32_t clip_heads;
+  int32_t clip_positions;
+  int32_t clip_act;             /* 0 = quick_gelu (CLIP-L), 1 = erf GELU (OpenCLIP bigG) */
+  int32_t reserved[1];
 } sdxe_config;
 
 typedef struct sdxe_engine sdxe_engine;
@@ -97,6 +105,15 @@ int sdxe_vae_decode(sdxe_engine* e, const void* z, void* out, int n, int h, int 
  * modules/sd_samplers_common.py:87-112 (images_tensor_to_samples), used by img2img init (modules/processing.py:1602-1757).
  * Engine kind SDXE_MODEL_VAE_ENCODER, weights "encoder.*" and "quant_conv.*". H, W multiples of 2^(num_levels-1) (8). */
 int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int w, int io_dtype, void* stream);
+
+/* CLIP text transformer (row N4): hidden_states[layer] of the causal text transformer, optionally through final_layer_norm
+ * — what `encode_with_transformers` needs (modules/sd_hijack_clip.py:351-360: last_hidden_state, or hidden_states[-skip]
+ * + final_layer_norm for CLIP_stop_at_last_layers; sgm for SDXL: hidden_states[11] / "penultimate", no final norm).
+ * tokens: int32 [n, T] (device), T <= clip_positions; layer in 1 .. clip_layers counts transformer layers applied;
+ * out: [n, T, clip_hidden] in io_dtype (the engine's 16-bit type or SDXE_F32). Engine kind SDXE_MODEL_CLIP_TEXT, weights
+ * with the Hugging Face names "text_model.embeddings.token_embedding.weight", "text_model.encoder.layers.N.*", ... */
+int sdxe_clip_forward(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
+                      void* stream);
 
 /* Execution-plan cache. A plan (buffers from the engine's pool, tensor maps, one CUDA graph) is built per input shape
  * (n, h, w, ctx_len) on first use and replayed afterwards; at most `max_plans` (default 8) are kept, least recently used

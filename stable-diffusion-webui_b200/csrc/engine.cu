@@ -96,6 +96,10 @@ struct VaeResW {
   int cin = 0, cout = 0;
 };
 
+struct ClipLayerW {  // CLIPEncoderLayer: LN1 -> q|k|v -> causal attention -> out_proj (+x) -> LN2 -> fc1 -> act -> fc2 (+x)
+  LinW qkv, out, fc1, fc2;   // layer_norm1 / layer_norm2 are folded into qkv / fc1
+};
+
 struct Buf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -153,6 +157,11 @@ struct sdxe_engine {
   std::vector<std::vector<VaeResW>> e_down_blocks;
   std::vector<LinW> e_down_conv;
   std::vector<LinW> v_up_conv;                    // per level (level 0 unused)
+  // CLIP text transformer
+  void* c_tok = nullptr;   // [vocab, C] 16-bit
+  void* c_pos = nullptr;   // [positions, C] 16-bit
+  std::vector<ClipLayerW> c_layers;
+  NormW c_final;
 
   // activation pool
   std::multimap<size_t, void*> free_list;
@@ -187,6 +196,7 @@ struct sdxe_engine {
   int build_unet();
   int build_vae();
   int build_vae_encoder();
+  int build_clip();
   int build_res(ResW& r, const std::string& p, int cin, int cout);
   int build_st(STW& s, const std::string& p, int C, int depth);
   int build_vae_res(VaeResW& r, const std::string& p, int cin, int cout);
@@ -900,6 +910,37 @@ int sdxe_engine::build_vae_encoder() {
 }
 
 // =================================================================================================================
+// CLIP text transformer weights (Hugging Face CLIPTextModel names; open_clip towers are renamed on the host)
+// =================================================================================================================
+int sdxe_engine::build_clip() {
+  const int C = cfg.clip_hidden, I = cfg.clip_intermediate, L = cfg.clip_layers;
+  const std::string tm = "text_model.";
+  c_tok = alloc16((size_t)cfg.clip_vocab * C);
+  c_pos = alloc16((size_t)cfg.clip_positions * C);
+  const RawWeight* wt = find(tm + "embeddings.token_embedding.weight", (int64_t)cfg.clip_vocab * C);
+  const RawWeight* wp = find(tm + "embeddings.position_embedding.weight", (int64_t)cfg.clip_positions * C);
+  if (!sizing && wt) ECHK(pack_weight_launch(wt->dev, wt->dtype, c_tok, PACK_PLAIN, cfg.clip_vocab, C, C, 0, bf16, 0));
+  if (!sizing && wp) ECHK(pack_weight_launch(wp->dev, wp->dtype, c_pos, PACK_PLAIN, cfg.clip_positions, C, C, 0, bf16, 0));
+  c_layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    ClipLayerW& w = c_layers[l];
+    const std::string p = tm + "encoder.layers." + std::to_string(l) + ".";
+    NormW ln1, ln2;
+    ECHK(pack_norm(ln1, p + "layer_norm1", C));
+    ECHK(pack_norm(ln2, p + "layer_norm2", C));
+    ECHK(pack_linear(w.qkv, {p + "self_attn.q_proj.weight", p + "self_attn.k_proj.weight", p + "self_attn.v_proj.weight"},
+                     {p + "self_attn.q_proj.bias", p + "self_attn.k_proj.bias", p + "self_attn.v_proj.bias"}, C, C, PACK_PLAIN));
+    ECHK(pack_linear(w.out, {p + "self_attn.out_proj.weight"}, {p + "self_attn.out_proj.bias"}, C, C, PACK_PLAIN));
+    ECHK(pack_linear(w.fc1, {p + "mlp.fc1.weight"}, {p + "mlp.fc1.bias"}, I, C, PACK_PLAIN));
+    ECHK(pack_linear(w.fc2, {p + "mlp.fc2.weight"}, {p + "mlp.fc2.bias"}, C, I, PACK_PLAIN));
+    ECHK(fold_layer_norm(w.qkv, ln1));
+    ECHK(fold_layer_norm(w.fc1, ln2));
+  }
+  ECHK(pack_norm(c_final, tm + "final_layer_norm", C));
+  return 0;
+}
+
+// =================================================================================================================
 // engine: activation pool
 // =================================================================================================================
 Buf sdxe_engine::alloc(size_t bytes) {
@@ -1336,6 +1377,98 @@ int build_vae_plan(sdxe_engine* e, Plan* p, int n, int h, int w) {
 // =================================================================================================================
 namespace {
 
+// hidden_states[layer] (optionally + final_layer_norm) of the text transformer for n sequences of T tokens
+int build_clip_plan(sdxe_engine* e, Plan* plan, int n, int T, int layer, int final_norm) {
+  const sdxe_config& cfg = e->cfg;
+  const int C = cfg.clip_hidden, I = cfg.clip_intermediate, H = cfg.clip_heads, d = C / H;
+  const int64_t M = (int64_t)n * T;
+  const bool b = e->bf16;
+  Builder B(e, plan);
+  Buf x = e->alloc((size_t)M * C * 2);
+  Builder::RowStats st;
+  st.buf = e->alloc((size_t)M * sizeof(float2));
+  st.p = (const float2*)st.buf.p;
+  st.parts = 1;
+  {
+    void* xp = x.p;
+    float2* sp = (float2*)st.buf.p;
+    const void *tok = e->c_tok, *pos = e->c_pos;
+    const int vocab = cfg.clip_vocab;
+    plan->pre.push_back([=](cudaStream_t s) {
+      count_launch();
+      return clip_embed_launch((const int32_t*)plan->x, tok, pos, xp, sp, (int)M, T, C, vocab, b, s);
+    });
+  }
+  const float scale = 1.0f / sqrtf((float)d);
+  for (int l = 0; l < layer; ++l) {
+    const ClipLayerW& w = e->c_layers[l];
+    Buf qkv = e->alloc((size_t)M * 3 * C * 2);
+    Builder::GemmOpt oq;
+    oq.ln_part = st.p; oq.ln_parts = st.parts;
+    ECHK(B.gemm(x.p, C, M, w.qkv, qkv.p, oq));
+    B.free_stats(st);
+    Buf att = e->alloc((size_t)M * C * 2);
+    {
+      const void* qp = qkv.p;
+      void* ap = att.p;
+      B.ops->push_back(OpRec([=](cudaStream_t s) { count_launch(); return causal_attn_small_launch(qp, ap, n, T, H, d, scale, b, s); }, K_ATTN,
+                             2.0 * n * H * (double)T * T * d, 2.0 * (double)M * 4 * C, "causal attn"));
+    }
+    e->release(qkv);
+    Buf x2 = e->alloc((size_t)M * C * 2);
+    Builder::GemmOpt oo;
+    oo.residual = x.p; oo.ldr = C; oo.emit = &st;
+    ECHK(B.gemm(att.p, C, M, w.out, x2.p, oo));
+    e->release(att);
+    e->release(x);
+    x = x2;
+    Buf hmid = e->alloc((size_t)M * I * 2);
+    Builder::GemmOpt o1;
+    o1.ln_part = st.p; o1.ln_parts = st.parts;
+    ECHK(B.gemm(x.p, C, M, w.fc1, hmid.p, o1));
+    B.free_stats(st);
+    {
+      void* hp = hmid.p;
+      const int mode = cfg.clip_act;
+      B.ops->push_back(OpRec([=](cudaStream_t s) { count_launch(); return act_inplace_launch(hp, M * (int64_t)I, mode, b, s); }, K_OTHER, 0.0,
+                             4.0 * (double)M * I, "clip act"));
+    }
+    Buf x3 = e->alloc((size_t)M * C * 2);
+    Builder::GemmOpt o2;
+    o2.residual = x.p; o2.ldr = C;
+    if (l + 1 < layer) o2.emit = &st;
+    ECHK(B.gemm(hmid.p, I, M, w.fc2, x3.p, o2));
+    e->release(hmid);
+    e->release(x);
+    x = x3;
+  }
+  if (layer == 0) B.free_stats(st);
+  Buf y = x;
+  if (final_norm) {
+    y = e->alloc((size_t)M * C * 2);
+    const void* xp = x.p;
+    void* yp = y.p;
+    const float *g = e->c_final.g, *bt = e->c_final.b;
+    B.ops->push_back(OpRec([=](cudaStream_t s) { count_launch(); return layer_norm_launch(xp, g, bt, yp, (int)M, C, 1e-5f, b, s); }, K_LNORM, 0.0,
+                           4.0 * (double)M * C, "final_layer_norm"));
+  }
+  {
+    const void* yp = y.p;
+    const int dt = e->dt;
+    plan->post.push_back([=](cudaStream_t s) {
+      count_launch();
+      if (plan->io_dtype == SDXE_F32) return cast_to_f32_launch(yp, dt, (float*)plan->out, M * (int64_t)C, false, b, s);
+      SDXE_CUDA_CHECK(cudaMemcpyAsync(plan->out, yp, (size_t)M * C * 2, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    });
+  }
+  return 0;
+}
+
+}  // namespace
+
+namespace {
+
 // Drop the least recently used plan: its graph is destroyed and the buffers it pinned go back to the pool; pool memory
 // beyond pool_limit is returned to the driver (largest blocks first).
 void evict_lru(sdxe_engine* e) {
@@ -1420,12 +1553,16 @@ int sdxe_create(const sdxe_config* cfg, sdxe_engine** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) EFAIL("sdxe_create: no CUDA device (this engine has no CPU path)");
   if (cfg->dtype != SDXE_F16 && cfg->dtype != SDXE_BF16) EFAIL("sdxe_create: dtype must be F16 or BF16");
-  if (cfg->num_levels < 1 || cfg->num_levels > SDXE_MAX_LEVELS) EFAIL("sdxe_create: num_levels");
+  if (cfg->kind != SDXE_MODEL_CLIP_TEXT && (cfg->num_levels < 1 || cfg->num_levels > SDXE_MAX_LEVELS)) EFAIL("sdxe_create: num_levels");
   if (cfg->kind == SDXE_MODEL_UNET) {
     if (cfg->model_channels % 32) EFAIL("sdxe_create: model_channels must be a multiple of 32");
     if (cfg->context_dim % 8) EFAIL("sdxe_create: context_dim % 8");
   } else if (cfg->kind == SDXE_MODEL_VAE_DECODER || cfg->kind == SDXE_MODEL_VAE_ENCODER) {
     if (cfg->vae_ch % 32) EFAIL("sdxe_create: vae_ch must be a multiple of 32");
+  } else if (cfg->kind == SDXE_MODEL_CLIP_TEXT) {
+    if (cfg->clip_hidden % 64 || cfg->clip_heads < 1 || cfg->clip_hidden % cfg->clip_heads || (cfg->clip_hidden / cfg->clip_heads) % 8 ||
+        cfg->clip_intermediate % 64 || cfg->clip_layers < 1 || cfg->clip_vocab < 2 || cfg->clip_positions < 1 || cfg->clip_positions > 128)
+      EFAIL("sdxe_create: CLIP text config");
   } else {
     EFAIL("sdxe_create: unknown model kind");
   }
@@ -1476,7 +1613,8 @@ int sdxe_finalize(sdxe_engine* e) {
     e->sizing = pass == 0;
     e->cursor = 0;
     e->missing.clear();
-    int rc = e->cfg.kind == SDXE_MODEL_UNET ? e->build_unet() : (e->cfg.kind == SDXE_MODEL_VAE_ENCODER ? e->build_vae_encoder() : e->build_vae());
+    int rc = e->cfg.kind == SDXE_MODEL_UNET ? e->build_unet()
+             : (e->cfg.kind == SDXE_MODEL_VAE_ENCODER ? e->build_vae_encoder() : (e->cfg.kind == SDXE_MODEL_CLIP_TEXT ? e->build_clip() : e->build_vae()));
     if (rc != 0) return -1;
     if (!e->missing.empty()) {
       std::string m = "sdxe_finalize: missing / mis-shaped weights: " + e->missing;
@@ -1514,6 +1652,18 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
   Plan* p = get_plan(e, key, [&](Plan* pl) { return build_unet_plan(e, pl, n, h, w, ctx_len); });
   if (!p) return -1;
   p->x = x; p->t = t; p->ctx = ctx; p->y = y; p->out = out; p->io_dtype = io_dtype;
+  return run_plan(e, p, (cudaStream_t)stream);
+}
+
+int sdxe_clip_forward(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
+                      void* stream) {
+  if (!e || !e->finalized || e->cfg.kind != SDXE_MODEL_CLIP_TEXT) EFAIL("sdxe_clip_forward: engine is not a finalized CLIP text model");
+  if (!tokens || !out || n <= 0 || T <= 0 || T > e->cfg.clip_positions || layer < 0 || layer > e->cfg.clip_layers) EFAIL("sdxe_clip_forward: bad argument");
+  if (io_dtype != e->dt && io_dtype != SDXE_F32) EFAIL("sdxe_clip_forward: out must be the engine's 16-bit type or fp32");
+  const std::string key = "c:" + std::to_string(n) + ":" + std::to_string(T) + ":" + std::to_string(layer) + ":" + std::to_string(final_norm ? 1 : 0);
+  Plan* p = get_plan(e, key, [&](Plan* pl) { return build_clip_plan(e, pl, n, T, layer, final_norm ? 1 : 0); });
+  if (!p) return -1;
+  p->x = tokens; p->out = out; p->io_dtype = io_dtype;
   return run_plan(e, p, (cudaStream_t)stream);
 }
 

@@ -791,6 +791,130 @@ int ln_fold_launch(void* w, int rows, int K, int ld, const float* gamma, const f
 }
 
 // =============================================================================================================
+// CLIP text encoder pieces (row N4: FrozenCLIPEmbedder / FrozenOpenCLIPEmbedder2 `transformer`,
+// modules/sd_hijack_clip.py:351-360, modules/sd_hijack_open_clip.py:29-71). 77-token sequences: launch-latency-sized
+// work, so plain CUDA-core kernels; the projections run on the tcgen05 GEMM with the LayerNorms folded in.
+// =============================================================================================================
+// x[m, :] = round16(tok[ids[m], :] + pos[m % T, :]); also the row's (sum, sum of squares) for the first folded LayerNorm.
+template <bool BF16>
+__global__ void clip_embed_kernel(const int32_t* __restrict__ ids, const typename T16<BF16>::type* __restrict__ tok,
+                                  const typename T16<BF16>::type* __restrict__ pos, typename T16<BF16>::type* __restrict__ x,
+                                  float2* __restrict__ stat, int M, int T, int C, int vocab) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  int id = ids[m];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const typename T16<BF16>::type* tr = tok + (size_t)id * C;
+  const typename T16<BF16>::type* pr = pos + (size_t)(m % T) * C;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const typename T16<BF16>::type v = T16<BF16>::from_f(T16<BF16>::to_f(tr[c]) + T16<BF16>::to_f(pr[c]));
+    x[(size_t)m * C + c] = v;
+    const float f = T16<BF16>::to_f(v);
+    s += f;
+    q = fmaf(f, f, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) stat[m] = make_float2(s, q);
+}
+int clip_embed_launch(const int32_t* ids, const void* tok, const void* pos, void* x, float2* stat, int M, int T, int C, int vocab,
+                      bool bf16, cudaStream_t s) {
+  const int blocks = (M * 32 + 255) / 256;
+  if (bf16) clip_embed_kernel<true><<<blocks, 256, 0, s>>>(ids, (const __nv_bfloat16*)tok, (const __nv_bfloat16*)pos, (__nv_bfloat16*)x, stat, M, T, C, vocab);
+  else clip_embed_kernel<false><<<blocks, 256, 0, s>>>(ids, (const __half*)tok, (const __half*)pos, (__half*)x, stat, M, T, C, vocab);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// Causal self-attention over short sequences: qkv [B*T, 3C] (q | k | v, heads contiguous inside each), one CTA per
+// (batch, head), K and V of the head in shared memory, one warp per query row (token t attends to tokens <= t), fp32 math.
+template <bool BF16>
+__global__ void __launch_bounds__(128) causal_attn_small_kernel(const typename T16<BF16>::type* __restrict__ qkv,
+                                                                typename T16<BF16>::type* __restrict__ out, int T, int H, int d, float scale) {
+  extern __shared__ float sm[];
+  const int C = H * d, ld = 3 * C;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  float* sK = sm;                    // [T][d + 1]
+  float* sV = sm + T * (d + 1);      // [T][d]
+  float* sQ = sV + T * d;            // [4 warps][d]
+  float* sP = sQ + 4 * d;            // [4 warps][T]
+  const typename T16<BF16>::type* base = qkv + (size_t)b * T * ld + h * d;
+  for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+    const int t = i / d, c = i - t * d;
+    sK[t * (d + 1) + c] = T16<BF16>::to_f(base[(size_t)t * ld + C + c]);
+    sV[t * d + c] = T16<BF16>::to_f(base[(size_t)t * ld + 2 * C + c]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = sQ + warp * d;
+  float* p = sP + warp * T;
+  for (int r = warp; r < T; r += 4) {
+    for (int c = lane; c < d; c += 32) q[c] = T16<BF16>::to_f(base[(size_t)r * ld + c]) * scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j <= r; j += 32) {
+      float a = 0.f;
+      for (int c = 0; c < d; ++c) a = fmaf(q[c], sK[j * (d + 1) + c], a);
+      p[j] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j <= r; j += 32) {
+      const float e = __expf(p[j] - mx);
+      p[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int c = lane; c < d; c += 32) {
+      float a = 0.f;
+      for (int j = 0; j <= r; ++j) a = fmaf(p[j], sV[j * d + c], a);
+      out[((size_t)b * T + r) * C + h * d + c] = T16<BF16>::from_f(a * inv);
+    }
+    __syncwarp();
+  }
+}
+int causal_attn_small_launch(const void* qkv, void* out, int B, int T, int H, int d, float scale, bool bf16, cudaStream_t s) {
+  const size_t smem = sizeof(float) * ((size_t)T * (d + 1) + (size_t)T * d + 4 * d + 4 * T);
+  if (smem > 96 * 1024) { set_last_error(__FILE__, __LINE__, "causal_attn_small: sequence too long"); return -1; }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(causal_attn_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(causal_attn_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  if (bf16) causal_attn_small_kernel<true><<<B * H, 128, smem, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, H, d, scale);
+  else causal_attn_small_kernel<false><<<B * H, 128, smem, s>>>((const __half*)qkv, (__half*)out, T, H, d, scale);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// in place: mode 0 quick_gelu x * sigmoid(1.702 x) (CLIP-L), mode 1 erf GELU (OpenCLIP bigG)
+template <bool BF16>
+__global__ void act_inplace_kernel(typename T16<BF16>::type* __restrict__ x, int64_t n, int mode) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = T16<BF16>::to_f(x[i]);
+    const float y = mode == 0 ? v / (1.f + __expf(-1.702f * v)) : gelu_erf_f(v);
+    x[i] = T16<BF16>::from_f(y);
+  }
+}
+int act_inplace_launch(void* x, int64_t n, int mode, bool bf16, cudaStream_t s) {
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
+  if (bf16) act_inplace_kernel<true><<<blocks, 256, 0, s>>>((__nv_bfloat16*)x, n, mode);
+  else act_inplace_kernel<false><<<blocks, 256, 0, s>>>((__half*)x, n, mode);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================================
 // sampler-step fusions (latents stay fp32, as in the reference: x comes from torch.randn fp32, modules/rng.py:19)
 // =============================================================================================================
 __global__ void denoiser_in_kernel(const float* __restrict__ x, const int32_t* __restrict__ src,

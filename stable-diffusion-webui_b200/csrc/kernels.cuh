@@ -34,6 +34,11 @@ int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int
 // out[m, n] = act(round16(sum_k in[m,k] * W[n,k] + b[n]) (+ add[m,n])), act = SiLU (rounded) if silu_out; in/out fp32; W 16-bit [N,K]
 int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
                          int M, int N, int K, bool silu_out, bool bf16, cudaStream_t s);
+// CLIP text encoder pieces (kernels.cu)
+int clip_embed_launch(const int32_t* ids, const void* tok, const void* pos, void* x, float2* stat, int M, int T, int C, int vocab,
+                      bool bf16, cudaStream_t s);
+int causal_attn_small_launch(const void* qkv, void* out, int B, int T, int H, int d, float scale, bool bf16, cudaStream_t s);
+int act_inplace_launch(void* x, int64_t n, int mode, bool bf16, cudaStream_t s);
 int cast_to_f32_launch(const void* src, int src_dtype, float* dst, int64_t n, bool round16, bool bf16, cudaStream_t s);
 
 // ---- weight repack (run once at finalize) -------------------------------------------------------------------

@@ -313,3 +313,69 @@ class VAEEncoderEngine(_EngineBase):
 
     __call__ = encode_moments
 
+
+
+@dataclass
+class CLIPTextSpec:
+    """transformers CLIPTextConfig as far as the text transformer needs it (CLIP-L defaults = SD1.x `cond_stage_model`)."""
+
+    vocab_size: int = 49408
+    hidden_size: int = 768
+    intermediate_size: int = 3072
+    num_layers: int = 12
+    num_heads: int = 12
+    max_positions: int = 77
+    act: str = "quick_gelu"   # "gelu" for the OpenCLIP bigG tower of SDXL
+
+    @staticmethod
+    def from_any(cfg) -> "CLIPTextSpec":
+        return CLIPTextSpec(**{k: getattr(cfg, k) for k in CLIPTextSpec.__dataclass_fields__ if hasattr(cfg, k)})
+
+    @staticmethod
+    def from_state_dict(sd, num_heads: Optional[int] = None, act: Optional[str] = None) -> "CLIPTextSpec":
+        tok = sd["text_model.embeddings.token_embedding.weight"]
+        layers = len({k.split(".")[3] for k in sd if k.startswith("text_model.encoder.layers.")})
+        hidden = int(tok.shape[1])
+        return CLIPTextSpec(vocab_size=int(tok.shape[0]), hidden_size=hidden,
+                            intermediate_size=int(sd["text_model.encoder.layers.0.mlp.fc1.weight"].shape[0]), num_layers=layers,
+                            num_heads=num_heads or hidden // 64, max_positions=int(sd["text_model.embeddings.position_embedding.weight"].shape[0]),
+                            act=act or ("quick_gelu" if hidden == 768 else "gelu"))
+
+
+class CLIPTextEngine(_EngineBase):
+    """The text transformer behind `encode_with_transformers` (modules/sd_hijack_clip.py:351-360): token ids in, hidden
+    states out. Weights by their Hugging Face names ("text_model.embeddings...", "text_model.encoder.layers.N...")."""
+
+    def __init__(self, spec: CLIPTextSpec, dtype: torch.dtype = torch.float16, device="cuda:0"):
+        cfg = L.SdxeConfig()
+        cfg.kind = L.SDXE_MODEL_CLIP_TEXT
+        cfg.dtype = _dtype_code(dtype)
+        cfg.clip_vocab, cfg.clip_hidden, cfg.clip_intermediate = spec.vocab_size, spec.hidden_size, spec.intermediate_size
+        cfg.clip_layers, cfg.clip_heads, cfg.clip_positions = spec.num_layers, spec.num_heads, spec.max_positions
+        if spec.act not in ("quick_gelu", "gelu"):
+            raise L.SdxeError(f"CLIP activation {spec.act!r} is not implemented")
+        cfg.clip_act = 0 if spec.act == "quick_gelu" else 1
+        self.spec = spec
+        super().__init__(cfg, dtype, device)
+
+    def load_state_dict(self, sd, prefix: str = "", only=("text_model.",)):
+        sd = {k: v for k, v in sd.items() if "position_ids" not in k}
+        return super().load_state_dict(sd, prefix, only)
+
+    def forward(self, tokens: torch.Tensor, layer: Optional[int] = None, final_norm: bool = True,
+                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """tokens [n, T] integer -> hidden_states[layer] ([n, T, C]; layer = number of transformer layers applied, default
+        all), through final_layer_norm when `final_norm`. Result in the engine's dtype (or fp32)."""
+        if tokens.dim() != 2:
+            raise L.SdxeError("tokens must be [n, T]")
+        n, T = tokens.shape
+        layer = self.spec.num_layers if layer is None else int(layer)
+        ids = tokens.to(device=self.device, dtype=torch.int32).contiguous()
+        odt = out_dtype or self.dtype
+        out = torch.empty(n, T, self.spec.hidden_size, dtype=odt, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sdxe_clip_forward(self._h, L.ptr(ids), L.ptr(out), n, T, layer, 1 if final_norm else 0,
+                                               L.torch_dtype_code(odt), L.current_stream()), "sdxe_clip_forward")
+        return out
+
+    __call__ = forward

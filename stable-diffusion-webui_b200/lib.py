@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdxe.so")
 
 SDXE_F16, SDXE_BF16, SDXE_F32 = 0, 1, 2
-SDXE_MODEL_UNET, SDXE_MODEL_VAE_DECODER, SDXE_MODEL_VAE_ENCODER = 0, 1, 2
+SDXE_MODEL_UNET, SDXE_MODEL_VAE_DECODER, SDXE_MODEL_VAE_ENCODER, SDXE_MODEL_CLIP_TEXT = 0, 1, 2, 3
 SDXE_MAX_LEVELS = 8
 
 
@@ -42,7 +42,14 @@ class SdxeConfig(ctypes.Structure):
         ("vae_ch", c_int32),
         ("vae_z_channels", c_int32),
         ("vae_out_ch", c_int32),
-        ("reserved", c_int32 * 8),
+        ("clip_vocab", c_int32),
+        ("clip_hidden", c_int32),
+        ("clip_intermediate", c_int32),
+        ("clip_layers", c_int32),
+        ("clip_heads", c_int32),
+        ("clip_positions", c_int32),
+        ("clip_act", c_int32),
+        ("reserved", c_int32 * 1),
     ]
 
 
@@ -60,6 +67,7 @@ SYMBOLS = {
     "sdxe_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdxe_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdxe_vae_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdxe_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdxe_set_plan_cache": (c_int, [c_void_p, c_int, c_int64]),
     "sdxe_pool_bytes": (c_int64, [c_void_p, POINTER(c_int64)]),
     "sdxe_profile": (c_int, [c_void_p, c_int]),

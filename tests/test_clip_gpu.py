@@ -1,0 +1,128 @@
+"""Row N4 on the GPU: the sdxe CLIP text transformer (sdxe_clip_forward) against oracle/clip.py — itself pinned to
+transformers.CLIPTextModel, the class the reference runs (tests/test_clip_oracle_cpu.py) — on identical random weights:
+every hidden state the webui can ask for (last / clip-skip through final_layer_norm, SDXL's un-normed hidden_states[11]),
+both activations, and the whole prompt -> conditioning path with emphasis and multiple chunks."""
+import re
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _models(cuda, cfg, dtype, act="quick_gelu", seed=3):
+    from oracle.clip import CLIPTextModel
+    from sdwebui_b200.engine import CLIPTextEngine, CLIPTextSpec
+
+    torch.manual_seed(seed)
+    m = CLIPTextModel(cfg).eval()
+    with torch.no_grad():  # default nn init gives near-zero residual updates: widen so that every layer matters
+        for n, p in m.named_parameters():
+            if p.ndim == 2 and "embedding" not in n:
+                p.mul_(3.0)
+            if n.endswith("bias"):
+                p.add_(0.05 * torch.randn_like(p))
+    if act == "gelu":
+        for layer in m.text_model.encoder.layers:
+            mlp = layer.mlp
+            mlp.forward = (lambda x, mlp=mlp: mlp.fc2(torch.nn.functional.gelu(mlp.fc1(x))))
+    m = m.to(cuda)
+    spec = CLIPTextSpec(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                        num_layers=cfg.num_layers, num_heads=cfg.num_heads, max_positions=cfg.max_positions, act=act)
+    eng = CLIPTextEngine(spec, dtype=dtype, device=cuda)
+    eng.load_state_dict(m.state_dict())
+    eng.finalize()
+    return m, eng
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("which", ["tiny", "clip_l", "gelu"])
+def test_clip_hidden_states(cuda, dtype, which):
+    from oracle.clip import CLIPTextConfig, tiny_clip_config
+
+    if which == "tiny":
+        cfg = tiny_clip_config()
+        cfg.hidden_size, cfg.num_heads, cfg.intermediate_size = 128, 2, 512  # head dim 64, as CLIP-L / bigG
+    elif which == "clip_l":
+        cfg = CLIPTextConfig()                                           # 12 layers x 768, 12 heads: the SD1.x encoder
+    else:
+        cfg = CLIPTextConfig(vocab_size=2000, hidden_size=256, intermediate_size=1024, num_layers=4, num_heads=4, id_start=1998, id_end=1999)
+    m, eng = _models(cuda, cfg, dtype, act="gelu" if which == "gelu" else "quick_gelu")
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, cfg.vocab_size - 2, (5, 77), generator=g)
+    ids[:, 0] = cfg.id_start
+    ids[0, 9:] = cfg.id_end
+    ids[3, 76] = cfg.id_end
+    with torch.no_grad():
+        hs = m.hidden_states(ids.to(cuda))
+        fin = m.text_model.final_layer_norm
+        L = cfg.num_layers
+        cases = {"last": (L, True, fin(hs[-1])), "clip skip 2": (L - 1, True, fin(hs[-2])), "hidden[L-1] no norm": (L - 1, False, hs[L - 1]),
+                 "embeddings": (0, False, hs[0])}
+        m16 = m.to(dtype)
+        hs16 = m16.hidden_states(ids.to(cuda))
+        ref16 = {"last": m16.text_model.final_layer_norm(hs16[-1]), "clip skip 2": m16.text_model.final_layer_norm(hs16[-2]),
+                 "hidden[L-1] no norm": hs16[L - 1], "embeddings": hs16[0]}
+    tol = 3e-3 if dtype == torch.float16 else 2e-2
+    for name, (layer, fnorm, want) in cases.items():
+        out = eng.forward(ids, layer=layer, final_norm=fnorm)
+        e, e_ref = rel_err(out, want), rel_err(ref16[name], want)
+        print(f"clip {which} {str(dtype)[6:]} {name}: sdxe {e:.3e}  torch {str(dtype)[6:]} {e_ref:.3e}")
+        assert out.shape == want.shape and e < max(2 * e_ref, tol), (name, e, e_ref)
+    # fp32 output path
+    out32 = eng.forward(ids, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32 and rel_err(out32, cases["last"][2]) < max(2 * rel_err(ref16["last"], cases["last"][2]), tol)
+    eng.close()
+
+
+def test_prompt_to_conditioning(cuda):
+    """FrozenCLIPEmbedderWithCustomWords.forward (chunks + emphasis + clip skip) vs oracle get_learned_conditioning."""
+    import types
+
+    from oracle.clip import CLIPTextConfig, CLIPTextModel, chunk_tokens, emphasis_original  # noqa: F401
+    from sdwebui_b200.prompt_parser import parse_prompt_attention
+    from sdwebui_b200.sd_hijack_clip import FrozenCLIPEmbedderForSDXLWithCustomWords, FrozenCLIPEmbedderWithCustomWords, TextOptions
+
+    cfg = CLIPTextConfig(vocab_size=3000, num_layers=3, id_start=2998, id_end=2999)
+    torch.manual_seed(5)
+    m = CLIPTextModel(cfg).eval().to(cuda)
+
+    def tok(texts, truncation=False, add_special_tokens=False):
+        return {"input_ids": [[7 if w == "," else 10 + (sum((i + 1) * ord(c) for i, c in enumerate(w)) % 2900) for w in re.findall(r"[A-Za-z0-9]+|,", t)] for t in texts]}
+
+    tokenizer = types.SimpleNamespace(__call__=tok, get_vocab=lambda: {",</w>": 7}, bos_token_id=cfg.id_start, eos_token_id=cfg.id_end)
+    tokenizer_callable = type("Tok", (), {"__call__": staticmethod(tok), "get_vocab": staticmethod(lambda: {",</w>": 7}),
+                                          "bos_token_id": cfg.id_start, "eos_token_id": cfg.id_end})()
+    for skip in (1, 2):
+        opts = TextOptions()
+        opts.CLIP_stop_at_last_layers = skip
+        emb = FrozenCLIPEmbedderWithCustomWords(m.state_dict(), tokenizer_callable, dtype=torch.float16, device=cuda, opts=opts)
+        prompts = ["a (red:1.4) crown, jeweled", " ".join(f"w{i}" for i in range(90)) + ", (tail:0.6)"]
+        z = emb.forward(prompts)
+        assert z.shape == (2, 154, 768)
+        # oracle: same chunks (taken from the product's own, reference-pinned tokenize_line), encoded chunk batch by chunk batch
+        bc, _ = emb.process_texts(prompts)
+        want = []
+        with torch.no_grad():
+            for i in range(2):
+                chunks = [c[i] if i < len(c) else emb.empty_chunk() for c in bc]
+                ids = torch.tensor([c.tokens for c in chunks], device=cuda)
+                mul = torch.tensor([c.multipliers for c in chunks], device=cuda)
+                want.append(emphasis_original(m.encode_with_transformers(ids, skip), mul))
+        want = torch.hstack(want)
+        e = rel_err(z, want)
+        print(f"prompt -> cond, clip skip {skip}: rel err {e:.3e}")
+        assert e < 4e-3
+        emb.close()
+    xl = FrozenCLIPEmbedderForSDXLWithCustomWords(m.state_dict(), tokenizer_callable, dtype=torch.float16, device=cuda, layer="hidden", layer_idx=2)
+    z = xl.forward(["plain prompt"])
+    with torch.no_grad():
+        ids = torch.tensor([xl.tokenize_line("plain prompt")[0][0].tokens], device=cuda)
+        want = m.hidden_states(ids)[2]
+    assert rel_err(z, want) < 4e-3
+    xl.close()

@@ -31,7 +31,14 @@ def rel_err(a, b):
 
 def _free():
     gc.collect()
+    torch.cuda.synchronize()
     torch.cuda.empty_cache()
+
+
+def _mem(tag):
+    free, total = torch.cuda.mem_get_info()
+    print(f"  [mem {tag}] device free {free / 2**30:.1f} / {total / 2**30:.1f} GiB, torch allocated {torch.cuda.memory_allocated() / 2**30:.1f} "
+          f"reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB")
 
 
 def _oracle_models(cuda, config, seed_u, seed_v):
@@ -104,6 +111,7 @@ def _txt2img_case(cuda, config, sp, B, dtypes, ctx_dim, adm, scale_factor):
         _free()
     del unet, vae
     _free()
+    _mem("before engines")
     for dt in dtypes:
         model = _engine_model(cuda, spec, usd, vsd, dt, is_sdxl=bool(adm))
         c = {"crossattn": cond, "vector": yc} if adm else cond

@@ -37,7 +37,7 @@ def test_config_struct_matches_header():
     fields = re.findall(r"int32_t\s+([a-z_]+)(\[[A-Z_0-9]+\])?;", body)
     py = [f[0] for f in L.SdxeConfig._fields_]
     assert [f[0] for f in fields] == py
-    n_ints = sum((8 if dim else 1) for _, dim in fields)
+    n_ints = sum((1 if not dim else (8 if dim == "[SDXE_MAX_LEVELS]" else int(dim[1:-1]))) for _, dim in fields)
     assert ctypes.sizeof(L.SdxeConfig) == 4 * n_ints
 
 
