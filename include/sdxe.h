@@ -166,6 +166,11 @@ int sdxe_cfg_combine(const float* x, const void* eps, const float* sigma, float 
 int sdxe_cfg_combine_multi(const float* x, const void* eps, const float* sigma, const int32_t* row_ptr,
                            const int32_t* cond_rows, const float* cond_w, const int32_t* uncond_rows, float* denoised,
                            int B, int64_t elems, int eps_dtype, void* stream);
+/* out = c0 p0 + c1 p1 + c2 p2 + c3 p3 over fp32 latents (p1..p3 may be NULL, out may alias an input): the step update of
+ * the remaining k-diffusion samplers (Euler, Heun, DPM2, DPM2 a, DPM++ 2S a, LMS, Restart; selected at
+ * modules/sd_samplers_kdiffusion.py:11-27) with the step's scalars computed on the host. */
+int sdxe_lincomb(float* out, const float* p0, float c0, const float* p1, float c1, const float* p2, float c2, const float* p3,
+                 float c3, int64_t total, void* stream);
 /* x <- x + (x - denoised)/sigma * (sigma_down - sigma) + noise * sigma_up  (noise may be NULL when sigma_up == 0). */
 int sdxe_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma, float sigma_down,
                               float sigma_up, int64_t total, void* stream);

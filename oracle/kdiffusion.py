@@ -154,6 +154,160 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None):
     return x
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# The other k-diffusion samplers the webui lists (modules/sd_samplers_kdiffusion.py:11-27), restated from
+# crowsonkb/k-diffusion@ab527a9a k_diffusion/sampling.py (un-vendored). noise_sampler() = p.rng.next() as above.
+# ----------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_euler(model, x, sigmas, extra_args=None, callback=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, noise_sampler=None):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + noise_sampler() * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in, **extra_args)
+        d = to_d(x, sigma_hat, denoised)
+        x = x + d * (sigmas[i + 1] - sigma_hat)
+    return x
+
+
+@torch.no_grad()
+def sample_heun(model, x, sigmas, extra_args=None, callback=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, noise_sampler=None):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + noise_sampler() * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in, **extra_args)
+        d = to_d(x, sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            denoised_2 = model(x_2, sigmas[i + 1] * s_in, **extra_args)
+            d_2 = to_d(x_2, sigmas[i + 1], denoised_2)
+            x = x + (d + d_2) / 2 * dt
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, noise_sampler=None):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + noise_sampler() * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in, **extra_args)
+        d = to_d(x, sigma_hat, denoised)
+        if sigmas[i + 1] == 0:
+            x = x + d * (sigmas[i + 1] - sigma_hat)
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigma_hat)
+            denoised_2 = model(x_2, sigma_mid * s_in, **extra_args)
+            d_2 = to_d(x_2, sigma_mid, denoised_2)
+            x = x + d_2 * (sigmas[i + 1] - sigma_hat)
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, eta=1.0, s_noise=1.0, noise_sampler=None):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = to_d(x, sigmas[i], denoised)
+        if sigma_down == 0:
+            x = x + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigmas[i])
+            denoised_2 = model(x_2, sigma_mid * s_in, **extra_args)
+            d_2 = to_d(x_2, sigma_mid, denoised_2)
+            x = x + d_2 * (sigma_down - sigmas[i])
+            x = x + noise_sampler() * s_noise * sigma_up
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, eta=1.0, s_noise=1.0, noise_sampler=None):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()  # noqa: E731
+    t_fn = lambda sigma: sigma.log().neg()  # noqa: E731
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if sigma_down == 0:
+            d = to_d(x, sigmas[i], denoised)
+            x = x + d * (sigma_down - sigmas[i])
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * denoised
+            denoised_2 = model(x_2, sigma_fn(s) * s_in, **extra_args)
+            x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_2
+        if sigmas[i + 1] > 0:
+            x = x + noise_sampler() * s_noise * sigma_up
+    return x
+
+
+def linear_multistep_coeff(order, t, i, j):
+    from scipy import integrate
+
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+@torch.no_grad()
+def sample_lms(model, x, sigmas, extra_args=None, callback=None, order=4):
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sigmas_cpu = sigmas.detach().cpu().numpy()
+    ds = []
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        d = to_d(x, sigmas[i], denoised)
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+        x = x + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+    return x
+
+
+def get_sigmas_exponential(n, sigma_min, sigma_max, device="cpu"):
+    sigmas = torch.linspace(math.log(sigma_max), math.log(sigma_min), n, device=device).exp()
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
+def get_sigmas_polyexponential(n, sigma_min, sigma_max, rho=1.0, device="cpu"):
+    ramp = torch.linspace(1, 0, n, device=device) ** rho
+    sigmas = torch.exp(ramp * (math.log(sigma_max) - math.log(sigma_min)) + math.log(sigma_min))
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
 def setup_img2img_steps(steps_requested: int, denoising_strength: float, steps_given: bool = True):
     """modules/sd_samplers_common.py:22-31. `steps_given` = the caller passed `steps` (the hires second pass does,
     :25-27); plain img2img does not and, with img2img_fix_steps off (the default), takes the else branch (:28-30)."""
@@ -166,11 +320,24 @@ def setup_img2img_steps(steps_requested: int, denoising_strength: float, steps_g
     return steps, t_enc
 
 
+SAMPLER_TABLE = {  # label -> (function name, default scheduler, discard_next_to_last_sigma); sd_samplers_kdiffusion.py:11-27
+    "Euler a": ("sample_euler_ancestral", None, False), "DPM++ 2M": ("sample_dpmpp_2m", "karras", False),
+    "DPM++ 2M Karras": ("sample_dpmpp_2m", "karras", False), "Euler": ("sample_euler", None, False),
+    "Heun": ("sample_heun", None, False), "LMS": ("sample_lms", None, False), "DPM2": ("sample_dpm_2", "karras", True),
+    "DPM2 a": ("sample_dpm_2_ancestral", "karras", True), "DPM++ 2S a": ("sample_dpmpp_2s_ancestral", "karras", False),
+}
+
+
 def webui_sigmas(schedule: DiscreteSchedule, sampler: str, steps: int) -> torch.Tensor:
-    """modules/sd_samplers_kdiffusion.py:79-132 with default options: 'Euler a' -> model_wrap.get_sigmas(steps);
-    'DPM++ 2M' -> its default scheduler 'karras' with the model's sigma_min / sigma_max, rho 7. CPU tensor."""
-    if sampler == "Euler a":
-        return schedule.get_sigmas(steps).cpu()
-    if sampler in ("DPM++ 2M", "DPM++ 2M Karras"):
-        return get_sigmas_karras(steps, schedule.sigmas[0].item(), schedule.sigmas[-1].item(), 7.0, "cpu")
-    raise ValueError(sampler)
+    """modules/sd_samplers_kdiffusion.py:79-132 with default options: samplers without a default scheduler ->
+    model_wrap.get_sigmas(steps); 'karras' -> the model's sigma_min / sigma_max, rho 7; discard_next_to_last_sigma samplers
+    ask for one more step and drop the penultimate sigma. CPU tensor."""
+    _, sched, discard = SAMPLER_TABLE[sampler]
+    n = steps + (1 if discard else 0)
+    if sched is None:
+        sig = schedule.get_sigmas(n).cpu()
+    else:
+        sig = get_sigmas_karras(n, schedule.sigmas[0].item(), schedule.sigmas[-1].item(), 7.0, "cpu")
+    if discard:
+        sig = torch.cat([sig[:-2], sig[-1:]])
+    return sig

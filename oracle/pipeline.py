@@ -56,10 +56,12 @@ class OraclePipeline:
         cfg = CFGDenoiser(self.model_wrap)
         extra = {"cond": cond, "uncond": uncond, "cond_scale": p.cfg_scale, "y_cond": y_cond, "y_uncond": y_uncond}
         sigmas = sigmas.to(x.device)
-        if p.sampler == "Euler a":
-            return K.sample_euler_ancestral(cfg, x, sigmas, extra_args=extra, eta=p.eta, s_noise=p.s_noise,
-                                            noise_sampler=rng.next)
-        return K.sample_dpmpp_2m(cfg, x, sigmas, extra_args=extra)
+        fn = getattr(K, K.SAMPLER_TABLE[p.sampler][0])
+        if fn in (K.sample_dpmpp_2m, K.sample_lms):
+            return fn(cfg, x, sigmas, extra_args=extra)
+        if fn in (K.sample_euler_ancestral, K.sample_dpm_2_ancestral, K.sample_dpmpp_2s_ancestral):
+            return fn(cfg, x, sigmas, extra_args=extra, eta=p.eta, s_noise=p.s_noise, noise_sampler=rng.next)
+        return fn(cfg, x, sigmas, extra_args=extra, s_noise=p.s_noise, noise_sampler=rng.next)  # Euler / Heun / DPM2 (s_churn 0)
 
     @torch.no_grad()
     def sample(self, p: SamplingParams, cond, uncond, y_cond=None, y_uncond=None):

@@ -142,6 +142,12 @@ int sdxe_cfg_combine(const float* x, const void* eps, const float* sigma, float 
                      int64_t elems, int eps_dtype, void* stream) {
   return cfg_combine_launch(x, eps, sigma, cond_scale, denoised, B, elems, eps_dtype, (cudaStream_t)stream);
 }
+int sdxe_lincomb(float* out, const float* p0, float c0, const float* p1, float c1, const float* p2, float c2, const float* p3,
+                 float c3, int64_t total, void* stream) {
+  if (!out || !p0 || total < 0) { set_last_error(__FILE__, __LINE__, "sdxe_lincomb: bad argument"); return -1; }
+  count_launch();
+  return lincomb_launch(out, p0, c0, p1, c1, p2, c2, p3, c3, total, (cudaStream_t)stream);
+}
 int sdxe_cfg_combine_multi(const float* x, const void* eps, const float* sigma, const int32_t* row_ptr,
                            const int32_t* cond_rows, const float* cond_w, const int32_t* uncond_rows, float* denoised,
                            int B, int64_t elems, int eps_dtype, void* stream) {

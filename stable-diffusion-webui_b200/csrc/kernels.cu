@@ -993,6 +993,26 @@ int cfg_combine_multi_launch(const float* x, const void* eps, const float* sigma
   return 0;
 }
 
+// out = c0 p0 + c1 p1 + c2 p2 + c3 p3 (null pointers skipped; out may alias any input): the update of every k-diffusion
+// sampler step is such a combination of x, denoised, a second denoised / derivative and noise, with host-side scalars.
+__global__ void lincomb_kernel(float* __restrict__ out, const float* p0, float c0, const float* p1, float c1, const float* p2,
+                               float c2, const float* p3, float c3, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float r = c0 * p0[i];
+    if (p1) r = fmaf(c1, p1[i], r);
+    if (p2) r = fmaf(c2, p2[i], r);
+    if (p3) r = fmaf(c3, p3[i], r);
+    out[i] = r;
+  }
+}
+int lincomb_launch(float* out, const float* p0, float c0, const float* p1, float c1, const float* p2, float c2, const float* p3, float c3,
+                   int64_t total, cudaStream_t s) {
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+  lincomb_kernel<<<blocks, 256, 0, s>>>(out, p0, c0, p1, c1, p2, c2, p3, c3, total);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void euler_a_step_kernel(float* __restrict__ x, const float* __restrict__ den, const float* __restrict__ noise,
                                     float inv_sigma, float dt, float sigma_up, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

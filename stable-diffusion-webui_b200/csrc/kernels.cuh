@@ -34,6 +34,8 @@ int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int
 // out[m, n] = act(round16(sum_k in[m,k] * W[n,k] + b[n]) (+ add[m,n])), act = SiLU (rounded) if silu_out; in/out fp32; W 16-bit [N,K]
 int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
                          int M, int N, int K, bool silu_out, bool bf16, cudaStream_t s);
+int lincomb_launch(float* out, const float* p0, float c0, const float* p1, float c1, const float* p2, float c2, const float* p3, float c3,
+                   int64_t total, cudaStream_t s);
 // CLIP text encoder pieces (kernels.cu)
 int clip_embed_launch(const int32_t* ids, const void* tok, const void* pos, void* x, float2* stat, int M, int T, int C, int vocab,
                       bool bf16, cudaStream_t s);

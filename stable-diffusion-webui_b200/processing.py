@@ -99,7 +99,11 @@ class StableDiffusionProcessingTxt2Img:
     width: int = 512
     height: int = 512
     eta: Optional[float] = None
+    s_churn: float = 0.0
+    s_tmin: float = 0.0
+    s_tmax: float = float("inf")
     s_noise: float = 1.0
+    hr_scheduler: Optional[str] = None
     s_min_uncond: float = 0.0
     randn_source: str = "GPU"
     subseeds: Optional[List[int]] = None     # modules/processing.py:949 — variation seeds, slerp-ed in at subseed_strength

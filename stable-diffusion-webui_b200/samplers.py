@@ -433,11 +433,273 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
     return x
 
 
-# label, function, aliases, options — the two samplers north_star names (sd_samplers_kdiffusion.py:11-27)
+def _lincomb(lib, out, terms, n):
+    """out = sum(c * p) over up to four (tensor, coefficient) terms — one fused launch (sdxe_lincomb)."""
+    terms = list(terms) + [(None, 0.0)] * (4 - len(terms))
+    (p0, c0), (p1, c1), (p2, c2), (p3, c3) = terms
+    L.check(lib.sdxe_lincomb(L.ptr(out), L.ptr(p0), float(c0), L.ptr(p1), float(c1), L.ptr(p2), float(c2), L.ptr(p3), float(c3), n,
+                             L.current_stream()), "sdxe_lincomb")
+    return out
+
+
+def _churn(sig, i, s_churn, s_tmin, s_tmax):
+    gamma = min(s_churn / (len(sig) - 1), 2 ** 0.5 - 1) if s_tmin <= sig[i] <= s_tmax else 0.0
+    return gamma, sig[i] * (gamma + 1)
+
+
+def _prep(x, sigmas, extra_args):
+    return ({} if extra_args is None else extra_args), L.load(), x.float().contiguous().clone(), [float(s) for s in sigmas]
+
+
+@torch.no_grad()
+def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"),
+                 s_noise=1.0, noise_sampler: Optional[Callable] = None):
+    """k-diffusion sample_euler: x += (x - D(x, sigma_hat)) / sigma_hat * (sigma_next - sigma_hat)."""
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    for i in range(len(sig) - 1):
+        gamma, sigma_hat = _churn(sig, i, s_churn, s_tmin, s_tmax)
+        if gamma > 0:
+            _lincomb(lib, x, [(x, 1.0), (noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous(), s_noise * (sigma_hat ** 2 - sig[i] ** 2) ** 0.5)], n)
+        denoised = model(x, s_in * sigma_hat, **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        r = sig[i + 1] / sigma_hat
+        _lincomb(lib, x, [(x, r), (denoised, 1.0 - r)], n)   # x + (x - den) / s * (s' - s)
+    return x
+
+
+@torch.no_grad()
+def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"),
+                s_noise=1.0, noise_sampler: Optional[Callable] = None):
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    x2 = torch.empty_like(x)
+    for i in range(len(sig) - 1):
+        gamma, sigma_hat = _churn(sig, i, s_churn, s_tmin, s_tmax)
+        if gamma > 0:
+            _lincomb(lib, x, [(x, 1.0), (noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous(), s_noise * (sigma_hat ** 2 - sig[i] ** 2) ** 0.5)], n)
+        denoised = model(x, s_in * sigma_hat, **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        dt = sig[i + 1] - sigma_hat
+        a = dt / sigma_hat                                     # d * dt = (x - den) * a
+        if sig[i + 1] == 0:
+            _lincomb(lib, x, [(x, 1.0 + a), (denoised, -a)], n)
+        else:
+            _lincomb(lib, x2, [(x, 1.0 + a), (denoised, -a)], n)
+            denoised_2 = model(x2, s_in * sig[i + 1], **extra_args).contiguous()
+            b = dt / sig[i + 1]                                # d_2 * dt = (x_2 - den_2) * b
+            # x + (d + d_2) / 2 * dt
+            _lincomb(lib, x, [(x, 1.0 + a / 2), (denoised, -a / 2), (x2, b / 2), (denoised_2, -b / 2)], n)
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"),
+                 s_noise=1.0, noise_sampler: Optional[Callable] = None):
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    x2 = torch.empty_like(x)
+    for i in range(len(sig) - 1):
+        gamma, sigma_hat = _churn(sig, i, s_churn, s_tmin, s_tmax)
+        if gamma > 0:
+            _lincomb(lib, x, [(x, 1.0), (noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous(), s_noise * (sigma_hat ** 2 - sig[i] ** 2) ** 0.5)], n)
+        denoised = model(x, s_in * sigma_hat, **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        if sig[i + 1] == 0:
+            a = (sig[i + 1] - sigma_hat) / sigma_hat
+            _lincomb(lib, x, [(x, 1.0 + a), (denoised, -a)], n)
+        else:
+            sigma_mid = math.exp(0.5 * (math.log(sigma_hat) + math.log(sig[i + 1])))
+            a = (sigma_mid - sigma_hat) / sigma_hat
+            _lincomb(lib, x2, [(x, 1.0 + a), (denoised, -a)], n)
+            denoised_2 = model(x2, s_in * sigma_mid, **extra_args).contiguous()
+            b = (sig[i + 1] - sigma_hat) / sigma_mid           # x + d_2 * dt_2, d_2 = (x_2 - den_2) / sigma_mid
+            _lincomb(lib, x, [(x, 1.0), (x2, b), (denoised_2, -b)], n)
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                           noise_sampler: Optional[Callable] = None):
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    x2 = torch.empty_like(x)
+    for i in range(len(sig) - 1):
+        denoised = model(x, s_in * sig[i], **extra_args).contiguous()
+        sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        if sigma_down == 0:
+            a = (sigma_down - sig[i]) / sig[i]
+            _lincomb(lib, x, [(x, 1.0 + a), (denoised, -a)], n)
+        else:
+            sigma_mid = math.exp(0.5 * (math.log(sig[i]) + math.log(sigma_down)))
+            a = (sigma_mid - sig[i]) / sig[i]
+            _lincomb(lib, x2, [(x, 1.0 + a), (denoised, -a)], n)
+            denoised_2 = model(x2, s_in * sigma_mid, **extra_args).contiguous()
+            b = (sigma_down - sig[i]) / sigma_mid
+            noise = noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous()
+            _lincomb(lib, x, [(x, 1.0), (x2, b), (denoised_2, -b), (noise, s_noise * sigma_up)], n)
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                              noise_sampler: Optional[Callable] = None):
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    x2 = torch.empty_like(x)
+    for i in range(len(sig) - 1):
+        denoised = model(x, s_in * sig[i], **extra_args).contiguous()
+        sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        noise = noise_sampler(sigmas[i], sigmas[i + 1]).float().contiguous() if sig[i + 1] > 0 else None
+        tail = [(noise, s_noise * sigma_up)] if noise is not None else []
+        if sigma_down == 0:
+            a = (sigma_down - sig[i]) / sig[i]
+            _lincomb(lib, x, [(x, 1.0 + a), (denoised, -a)] + tail, n)
+        else:
+            t, t_next = -math.log(sig[i]), -math.log(sigma_down)
+            h = t_next - t
+            s_mid = t + 0.5 * h
+            _lincomb(lib, x2, [(x, math.exp(-s_mid) / math.exp(-t)), (denoised, -math.expm1(-h * 0.5))], n)
+            denoised_2 = model(x2, s_in * math.exp(-s_mid), **extra_args).contiguous()
+            _lincomb(lib, x, [(x, math.exp(-t_next) / math.exp(-t)), (denoised_2, -math.expm1(-h))] + tail, n)
+    return x
+
+
+def linear_multistep_coeff(order, t, i, j):
+    from scipy import integrate
+
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j != k:
+                prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+@torch.no_grad()
+def sample_lms(model, x, sigmas, extra_args=None, callback=None, disable=None, order=4):
+    extra_args, lib, x, sig = _prep(x, sigmas, extra_args)
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    t_cpu = sigmas.detach().cpu().numpy()
+    ds = []
+    for i in range(len(sig) - 1):
+        denoised = model(x, s_in * sig[i], **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        d = torch.empty_like(x)
+        _lincomb(lib, d, [(x, 1.0 / sig[i]), (denoised, -1.0 / sig[i])], n)   # to_d
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        cur = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur, t_cpu, i, j) for j in range(cur)]
+        hist = list(reversed(ds))[:cur]
+        _lincomb(lib, x, [(x, 1.0)] + [(d_j, c_j) for c_j, d_j in zip(coeffs[:3], hist[:3])], n)
+        if cur == 4:
+            _lincomb(lib, x, [(x, 1.0), (hist[3], coeffs[3])], n)
+    return x
+
+
+@torch.no_grad()
+def restart_sampler(model, x, sigmas, extra_args=None, callback=None, disable=None, s_noise=1.0, restart_list=None,
+                    noise_sampler: Optional[Callable] = None):
+    """modules/sd_samplers_extra.py:7-74 ("Restart Sampling for Improving Generative Processes"): Heun steps over a Karras
+    schedule with restart segments that re-noise the sample back up to sigma 2. restart_list: {min_sigma: [steps, times,
+    max_sigma]}; None picks it from the step count exactly as the reference does. The re-noising draw is
+    `k_diffusion.sampling.torch.randn_like` in the reference, i.e. TorchHijack -> p.rng.next() = noise_sampler here."""
+    from . import sd_schedulers
+
+    extra_args = {} if extra_args is None else extra_args
+    lib = L.load()
+    x = x.float().contiguous().clone()
+    s_in, n = x.new_ones([x.shape[0]]), x.numel()
+    x2 = torch.empty_like(x)
+    step_id = 0
+
+    def heun_step(old_sigma, new_sigma, second_order=True):
+        nonlocal step_id
+        old, new = float(old_sigma), float(new_sigma)
+        denoised = model(x, s_in * old, **extra_args).contiguous()
+        if callback is not None:
+            callback({"x": x, "i": step_id, "sigma": new_sigma, "sigma_hat": old_sigma, "denoised": denoised})
+        dt = new - old
+        a = dt / old
+        if new == 0 or not second_order:
+            _lincomb(lib, x, [(x, 1.0 + a), (denoised, -a)], n)
+        else:
+            _lincomb(lib, x2, [(x, 1.0 + a), (denoised, -a)], n)
+            denoised_2 = model(x2, s_in * new, **extra_args).contiguous()
+            b = dt / new
+            _lincomb(lib, x, [(x, 1.0 + a / 2), (denoised, -a / 2), (x2, b / 2), (denoised_2, -b / 2)], n)
+        step_id += 1
+
+    steps = sigmas.shape[0] - 1
+    if restart_list is None:
+        if steps >= 20:
+            restart_steps, restart_times = 9, 1
+            if steps >= 36:
+                restart_steps, restart_times = steps // 4, 2
+            sigmas = sd_schedulers.get_sigmas_karras(steps - restart_steps * restart_times, sigmas[-2].item(), sigmas[0].item(), device=sigmas.device)
+            restart_list = {0.1: [restart_steps + 1, restart_times, 2]}
+        else:
+            restart_list = {}
+    restart_list = {int(torch.argmin(abs(sigmas - key), dim=0)): value for key, value in restart_list.items()}
+    step_list = []
+    for i in range(len(sigmas) - 1):
+        step_list.append((sigmas[i], sigmas[i + 1]))
+        if i + 1 in restart_list:
+            restart_steps, restart_times, restart_max = restart_list[i + 1]
+            min_idx = i + 1
+            max_idx = int(torch.argmin(abs(sigmas - restart_max), dim=0))
+            if max_idx < min_idx:
+                sigma_restart = sd_schedulers.get_sigmas_karras(restart_steps, sigmas[min_idx].item(), sigmas[max_idx].item(), device=sigmas.device)[:-1]
+                while restart_times > 0:
+                    restart_times -= 1
+                    step_list.extend(zip(sigma_restart[:-1], sigma_restart[1:]))
+    last_sigma = None
+    for old_sigma, new_sigma in step_list:
+        if last_sigma is None:
+            last_sigma = old_sigma
+        elif last_sigma < old_sigma:
+            noise = noise_sampler(last_sigma, old_sigma).float().contiguous()
+            _lincomb(lib, x, [(x, 1.0), (noise, s_noise * float(old_sigma ** 2 - last_sigma ** 2) ** 0.5)], n)
+        heun_step(old_sigma, new_sigma)
+        last_sigma = new_sigma
+    return x
+
+
+# label, function, aliases, options — modules/sd_samplers_kdiffusion.py:11-27. The SDE family (DPM++ SDE / 2M SDE / 3M SDE:
+# BrownianTreeNoiseSampler over torchsde) and DPM fast / adaptive are not mirrored.
 samplers_k_diffusion = [
     ("DPM++ 2M", sample_dpmpp_2m, ["k_dpmpp_2m"], {"scheduler": "karras"}),
+    ("DPM++ 2S a", sample_dpmpp_2s_ancestral, ["k_dpmpp_2s_a"], {"scheduler": "karras", "uses_ensd": True, "second_order": True}),
     ("Euler a", sample_euler_ancestral, ["k_euler_a", "k_euler_ancestral"], {"uses_ensd": True}),
+    ("Euler", sample_euler, ["k_euler"], {}),
+    ("LMS", sample_lms, ["k_lms"], {}),
+    ("Heun", sample_heun, ["k_heun"], {"second_order": True}),
+    ("DPM2", sample_dpm_2, ["k_dpm_2"], {"scheduler": "karras", "discard_next_to_last_sigma": True, "second_order": True}),
+    ("DPM2 a", sample_dpm_2_ancestral, ["k_dpm_2_a"], {"scheduler": "karras", "discard_next_to_last_sigma": True, "uses_ensd": True, "second_order": True}),
+    ("Restart", restart_sampler, ["restart"], {"scheduler": "karras", "second_order": True}),
 ]
+sampler_extra_params = {  # modules/sd_samplers_kdiffusion.py:36-46
+    sample_euler: ["s_churn", "s_tmin", "s_tmax", "s_noise"],
+    sample_heun: ["s_churn", "s_tmin", "s_tmax", "s_noise"],
+    sample_dpm_2: ["s_churn", "s_tmin", "s_tmax", "s_noise"],
+    sample_dpm_2_ancestral: ["s_noise"],
+    sample_dpmpp_2s_ancestral: ["s_noise"],
+}
 _sampler_map = {}
 for _label, _fn, _aliases, _opts in samplers_k_diffusion:
     _sampler_map[_label.lower()] = (_label, _fn, _opts)
@@ -446,15 +708,29 @@ for _label, _fn, _aliases, _opts in samplers_k_diffusion:
 _sampler_map["dpm++ 2m karras"] = _sampler_map["dpm++ 2m"]  # pre-1.9 name (infotext compatibility)
 
 
+class SchedulerOptions:
+    """the `shared.opts` fields get_sigmas reads (defaults of modules/shared_options.py)."""
+
+    always_discard_next_to_last_sigma = False
+    use_old_karras_scheduler_sigmas = False
+    sigma_min = 0.0
+    sigma_max = 0.0
+    rho = 0.0
+    beta_dist_alpha = 0.6
+    beta_dist_beta = 0.6
+    sgm_noise_multiplier = False
+
+
 class KDiffusionSampler:
     def __init__(self, funcname_or_label, sd_model, options=None):
         key = funcname_or_label.lower() if isinstance(funcname_or_label, str) else None
         if key not in _sampler_map:
-            raise L.SdxeError(f"sampler {funcname_or_label!r} is not accelerated (available: Euler a, DPM++ 2M)")
+            raise L.SdxeError(f"sampler {funcname_or_label!r} is not mirrored (available: " + ", ".join(x[0] for x in samplers_k_diffusion) + ")")
         self.label, self.func, self.options = _sampler_map[key]
         if options:
             self.options = {**self.options, **options}
         self.sd_model = sd_model
+        self.sched_opts = SchedulerOptions()
         self.model_wrap_cfg = CFGDenoiser(self)
         self.model_wrap = self.model_wrap_cfg.inner_model
         self.last_latent = None
@@ -464,34 +740,68 @@ class KDiffusionSampler:
         self.p = None
         self.sampler_extra_args = None
 
-    # -- sigma schedule (sd_samplers_kdiffusion.py:79-132 with default options) --------------------------------
+    # -- sigma schedule (modules/sd_samplers_kdiffusion.py:79-132) ------------------------------------------------
     def get_sigmas(self, p, steps: int) -> torch.Tensor:
-        scheduler_name = getattr(p, "scheduler", None) or "Automatic"
+        from . import sd_schedulers
+
+        o = self.sched_opts
+        discard = bool(self.options.get("discard_next_to_last_sigma", False)) or o.always_discard_next_to_last_sigma
+        steps += 1 if discard else 0
+        scheduler_name = (getattr(p, "hr_scheduler", None) if getattr(p, "is_hr_pass", False) else getattr(p, "scheduler", None)) or "Automatic"
         if scheduler_name == "Automatic":
             scheduler_name = self.options.get("scheduler", None)
+        scheduler = sd_schedulers.schedulers_map.get(scheduler_name)
+        if scheduler is None and scheduler_name is not None:
+            raise L.SdxeError(f"unknown scheduler {scheduler_name!r}")
         m_sigma_min, m_sigma_max = self.model_wrap.sigmas[0].item(), self.model_wrap.sigmas[-1].item()
-        if scheduler_name is None or scheduler_name.lower() in ("uniform",):
+        sigma_min, sigma_max = (0.1, 10) if o.use_old_karras_scheduler_sigmas else (m_sigma_min, m_sigma_max)
+        override = getattr(p, "sampler_noise_scheduler_override", None)
+        if override:
+            sigmas = override(steps)
+        elif scheduler is None or scheduler.function is None:
             sigmas = self.model_wrap.get_sigmas(steps)
-        elif scheduler_name.lower() == "karras":
-            sigmas = get_sigmas_karras(n=steps, sigma_min=m_sigma_min, sigma_max=m_sigma_max, rho=7.0, device="cpu")
         else:
-            raise L.SdxeError(f"scheduler {scheduler_name!r} is not mirrored")
+            kw = {"sigma_min": sigma_min, "sigma_max": sigma_max}
+            if o.sigma_min != 0 and o.sigma_min != m_sigma_min:
+                kw["sigma_min"] = o.sigma_min
+            if o.sigma_max != 0 and o.sigma_max != m_sigma_max:
+                kw["sigma_max"] = o.sigma_max
+            if scheduler.default_rho != -1 and o.rho != 0 and o.rho != scheduler.default_rho:
+                kw["rho"] = o.rho
+            if scheduler.need_inner_model:
+                kw["inner_model"] = self.model_wrap
+            if scheduler.name == "align_your_steps":
+                kw["is_sdxl"] = bool(getattr(self.sd_model, "is_sdxl", False))
+            if scheduler.name == "beta":
+                kw["alpha"], kw["beta"] = o.beta_dist_alpha, o.beta_dist_beta
+            sigmas = scheduler.function(n=steps, **kw, device="cpu")
+        if discard:
+            sigmas = torch.cat([sigmas[:-2], sigmas[-1:]])
         return sigmas.cpu()
 
     def initialize(self, p) -> dict:
+        """modules/sd_samplers_common.py:288-333: per-job state + the sampler function's optional arguments."""
+        import inspect
+
         self.p = p
         cfg = self.model_wrap_cfg
         cfg.p = p
         cfg.mask = getattr(p, "mask", None)
         cfg.nmask = getattr(p, "nmask", None)
         cfg.step = 0
-        self.eta = p.eta if getattr(p, "eta", None) is not None else 1.0
+        self.eta = p.eta if getattr(p, "eta", None) is not None else 1.0  # opts.eta_ancestral default
         self.s_min_uncond = getattr(p, "s_min_uncond", 0.0)
+        params = inspect.signature(self.func).parameters
         kw = {}
-        if self.func is sample_euler_ancestral:
+        for name in sampler_extra_params.get(self.func, []):
+            if hasattr(p, name) and name in params:
+                kw[name] = getattr(p, name)
+        if "s_tmax" in kw and not kw["s_tmax"]:
+            kw["s_tmax"] = float("inf")  # 0 = inf
+        if "eta" in params:
             kw["eta"] = self.eta
-            kw["s_noise"] = getattr(p, "s_noise", 1.0)
-            kw["noise_sampler"] = lambda sigma, sigma_next: p.rng.next()  # TorchHijack.randn_like
+        if "noise_sampler" in params:
+            kw["noise_sampler"] = lambda sigma, sigma_next: p.rng.next()  # TorchHijack.randn_like -> p.rng.next()
         return kw
 
     def launch_sampling(self, steps, func):
@@ -510,7 +820,10 @@ class KDiffusionSampler:
     def sample(self, p, x, conditioning, unconditional_conditioning, steps=None, image_conditioning=None):
         steps = steps or p.steps
         sigmas = self.get_sigmas(p, steps)
-        x = x * sigmas[0]
+        if self.sched_opts.sgm_noise_multiplier:
+            x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+        else:
+            x = x * sigmas[0]
         extra = self.initialize(p)
         self.last_latent = x
         self.sampler_extra_args = {"cond": conditioning, "image_cond": image_conditioning, "uncond": unconditional_conditioning,

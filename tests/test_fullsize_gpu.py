@@ -41,21 +41,32 @@ def _mem(tag):
           f"reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB")
 
 
-def _oracle_models(cuda, config, seed_u, seed_v):
-    """fp32 oracle UNet + VAE decoder with the seeded synthetic weights of sdwebui_b200.checkpoint (generated on the GPU)."""
-    from oracle.unet import UNetModel, sd15_config, sdxl_config
-    from oracle.vae import AutoencoderKLDecode, VAEConfig
+def _state_dicts(cuda, config, seed_u, seed_v):
+    """Seeded synthetic fp32 weights (sdwebui_b200.checkpoint), generated on the GPU."""
     from sdwebui_b200 import checkpoint as C
     from sdwebui_b200.engine import UNetSpec, VAESpec
 
     spec = UNetSpec.sd15() if config == "sd15" else UNetSpec.sdxl()
     usd = C.synthetic_state_dict(C.unet_param_shapes(spec), seed=seed_u, device=cuda, dtype=torch.float32)
     vsd = C.synthetic_state_dict(C.vae_decoder_param_shapes(VAESpec()), seed=seed_v, device=cuda, dtype=torch.float32)
+    return spec, usd, vsd
+
+
+def _oracle_from(cuda, config, usd, vsd):
+    from oracle.unet import UNetModel, sd15_config, sdxl_config
+    from oracle.vae import AutoencoderKLDecode, VAEConfig
+
     with torch.device(cuda):
         unet = UNetModel(sd15_config() if config == "sd15" else sdxl_config()).eval()
         vae = AutoencoderKLDecode(VAEConfig()).eval()
     unet.load_state_dict(usd)
     vae.load_state_dict(vsd)
+    return unet, vae
+
+
+def _oracle_models(cuda, config, seed_u, seed_v):
+    spec, usd, vsd = _state_dicts(cuda, config, seed_u, seed_v)
+    unet, vae = _oracle_from(cuda, config, usd, vsd)
     return spec, unet, vae, usd, vsd
 
 
@@ -91,27 +102,18 @@ def _report(tag, lat, img, lat32, img32):
 
 
 def _txt2img_case(cuda, config, sp, B, dtypes, ctx_dim, adm, scale_factor):
+    """The engines run FIRST: they take their memory from cudaMalloc, and after a full-size fp32 oracle run the PyTorch
+    caching allocator keeps > 150 GB reserved (fragmented segments that empty_cache() cannot return)."""
     from oracle.pipeline import OraclePipeline
     from oracle.synth import synthetic_context, synthetic_vector
     from sdwebui_b200.processing import StableDiffusionProcessingTxt2Img, process_images
 
-    spec, unet, vae, usd, vsd = _oracle_models(cuda, config, 21, 22)
+    spec, usd, vsd = _state_dicts(cuda, config, 21, 22)
     cond = synthetic_context(B, 77, ctx_dim, 3, cuda)
     uncond = synthetic_context(B, 77, ctx_dim, 4, cuda)
     yc = synthetic_vector(B, adm, 5, cuda) if adm else None
     yu = synthetic_vector(B, adm, 6, cuda) if adm else None
-    lat32, img32 = OraclePipeline(unet, vae, cuda, dtype_unet=torch.float32).txt2img(sp, cond, uncond, yc, yu)
-    img32 = img32.cpu()
-    res = {}
-    for dt in dtypes:
-        p16 = _torch16(unet, vae, cuda, dt)
-        lat_r, img_r = p16.txt2img(sp, cond, uncond, yc, yu)
-        res[("ref", dt)] = _report(f"torch {str(dt)[6:]}", lat_r, img_r.cpu(), lat32, img32)
-        del p16
-        _free()
-    del unet, vae
-    _free()
-    _mem("before engines")
+    eng_out = {}
     for dt in dtypes:
         model = _engine_model(cuda, spec, usd, vsd, dt, is_sdxl=bool(adm))
         c = {"crossattn": cond, "vector": yc} if adm else cond
@@ -122,12 +124,27 @@ def _txt2img_case(cuda, config, sp, B, dtypes, ctx_dim, adm, scale_factor):
                                              denoising_strength=sp.denoising_strength)
         model.scale_factor = scale_factor
         out = process_images(p)
-        img = out.images.permute(0, 3, 1, 2).float() / 255.0
-        res[("eng", dt)] = _report(f"sdxe {str(dt)[6:]}", out.latents, img, lat32, img32)
+        eng_out[dt] = (out.latents.float().cpu(), out.images.permute(0, 3, 1, 2).float() / 255.0)
         model.unet.deactivate()
         model.vae.close()
-        del model
+        del model, out
         _free()
+    unet, vae = _oracle_from(cuda, config, usd, vsd)
+    del usd, vsd
+    _free()
+    lat32, img32 = OraclePipeline(unet, vae, cuda, dtype_unet=torch.float32).txt2img(sp, cond, uncond, yc, yu)
+    lat32, img32 = lat32.cpu(), img32.cpu()
+    res = {}
+    for dt in dtypes:
+        p16 = _torch16(unet, vae, cuda, dt)
+        lat_r, img_r = p16.txt2img(sp, cond, uncond, yc, yu)
+        res[("ref", dt)] = _report(f"torch {str(dt)[6:]}", lat_r.cpu(), img_r.cpu(), lat32, img32)
+        del p16
+        _free()
+    del unet, vae
+    _free()
+    for dt in dtypes:
+        res[("eng", dt)] = _report(f"sdxe {str(dt)[6:]}", eng_out[dt][0], eng_out[dt][1], lat32, img32)
     for dt in dtypes:
         e, ps = res[("eng", dt)]
         e_ref, _ = res[("ref", dt)]
