@@ -115,6 +115,13 @@ int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int 
 int sdxe_clip_forward(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
                       void* stream);
 
+/* Cross-attention K / V cache. The context of a job does not change between sampler steps (CFGDenoiser.forward re-sends the
+ * same cond_in every step, modules/sd_samplers_cfg_denoiser.py:236-249), but its k | v projections (one GEMM over all
+ * transformer blocks) would be recomputed by every sdxe_unet_forward call. A non-zero `key` set before a call promises that
+ * whatever context is passed under this key has identical contents each time; calls whose plan last projected the context
+ * under the same key skip the cast + GEMM. key = 0 (default) disables the cache. */
+int sdxe_unet_set_context_key(sdxe_engine* e, int64_t key);
+
 /* Execution-plan cache. A plan (buffers from the engine's pool, tensor maps, one CUDA graph) is built per input shape
  * (n, h, w, ctx_len) on first use and replayed afterwards; at most `max_plans` (default 8) are kept, least recently used
  * evicted, and after an eviction free pool memory beyond `pool_limit_mb` (default 6144; < 0 = keep) returns to the

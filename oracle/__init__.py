@@ -9,15 +9,22 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 only as the checker / reported baseline — never as the thing measured or shipped. The product
 (stable-diffusion-webui_b200/) does not import it and fails loudly without its CUDA library.
 
-PARITY PINNING STATUS: "parity unpinned" at the UNet / VAE / sampler level. The arithmetic of this path lives in three
-un-vendored upstream repositories that are absent from /root/reference (modules/launch_utils.py:355-357 pins
-Stability-AI/stablediffusion@cf1d67a6 `ldm`, Stability-AI/generative-models@45c443b3 `sgm`,
-crowsonkb/k-diffusion@ab527a9a `k_diffusion`), and the reference's own tests assert only HTTP 200 with all-zero
-weights (test/test_txt2img.py:43-90). What IS pinned, by tests/test_oracle_cpu.py:
-  * the Philox RNG against the reference's known-answer vector (modules/rng_philox.py:5-15) and against the reference
-    module itself imported from /root/reference (fixture generated by tests/golden/make_golden.py);
-  * exact parameter counts of the restated architectures: 859,520,964 (SD1.5 UNet), 2,567,463,684 (SDXL-base UNet),
-    49,490,179 (+20 post_quant_conv) (KL-VAE decoder) — SURVEY.md §8(c);
-  * the sigma table end points the reference quotes (modules/sd_schedulers.py:59-63: 14.615 / 0.029).
+PARITY PINNING STATUS. The arithmetic of this path lives in three un-vendored upstream repositories that are absent from
+/root/reference (modules/launch_utils.py:355-357 pins Stability-AI/stablediffusion@cf1d67a6 `ldm`,
+Stability-AI/generative-models@45c443b3 `sgm`, crowsonkb/k-diffusion@ab527a9a `k_diffusion`), and the reference's own tests
+assert only HTTP 200 with all-zero weights (test/test_txt2img.py:43-90). The reference does, however, keep its own copies
+of several pieces in-tree; each is EXECUTED unmodified by a committed generator (tests/golden/make_golden*.py, stub
+`modules.*` packages) and the oracle is held to its output:
+  PINNED to reference code
+  * KL-VAE decoder / encoder (vae.py)            <- modules/models/sd3/sd3_impls.py:171-355 (VAEDecoder / VAEEncoder, z = 4)
+  * CrossAttention.forward, VAE AttnBlock.forward <- modules/sd_hijack_optimizations.py (sdp, Doggettx, sub-quad, v1, InvokeAI)
+  * timestep_embedding, SpatialTransformer.forward <- modules/sd_hijack_unet.py:58-102
+  * combine_denoised (weights != 1)               <- modules/sd_samplers_cfg_denoiser.py:74-82
+  * Philox RNG, ImageRNG                          <- modules/rng_philox.py (+ known-answer vector :5-15), modules/rng.py
+  * Restart sampler, all noise schedules          <- modules/sd_samplers_extra.py, modules/sd_schedulers.py
+  * CLIP-L text transformer (clip.py)             <- transformers.CLIPTextModel, the class the reference calls
+  * exact parameter counts 859,520,964 / 2,567,463,684 / 49,490,179 (+20); sigma table end points (sd_schedulers.py:59-63)
+  UNPINNED ("parity unpinned" for these): the UNet assembly (ResBlock wiring, level structure: unet.py) and the k-diffusion
+  step formulas other than Restart (kdiffusion.py), restated from the published upstream sources.
 Each function cites the reference file:line (or upstream module) it follows.
 """

@@ -219,8 +219,10 @@ class UNetEngine(_EngineBase):
         super().__init__(cfg, dtype, device)
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor, y: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """eps = UNet(x, t, context[, y]); all tensors share x.dtype (fp16 / bf16 / fp32), x is [n,4,h,w] NCHW."""
+                out: Optional[torch.Tensor] = None, context_key: int = 0) -> torch.Tensor:
+        """eps = UNet(x, t, context[, y]); all tensors share x.dtype (fp16 / bf16 / fp32), x is [n,4,h,w] NCHW.
+        `context_key` != 0: the caller's promise that `context` has the contents it had the last time this key was
+        used — the cross-attention k | v projections are then reused (sdxe_unet_set_context_key)."""
         if not x.is_cuda:
             raise L.SdxeError("sdxe UNet needs CUDA tensors: there is no CPU fallback")
         dt = x.dtype
@@ -231,6 +233,7 @@ class UNetEngine(_EngineBase):
         n, _, h, w = x.shape
         if out is None:
             out = torch.empty_like(x)
+        L.check(self.lib.sdxe_unet_set_context_key(self._h, int(context_key)), "sdxe_unet_set_context_key")
         L.check(self.lib.sdxe_unet_forward(self._h, L.ptr(x), L.ptr(t), L.ptr(ctx), L.ptr(yy), L.ptr(out), n, h, w,
                                            ctx.shape[1], L.torch_dtype_code(dt), L.current_stream()), "sdxe_unet_forward")
         return out

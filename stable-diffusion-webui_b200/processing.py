@@ -48,9 +48,11 @@ class SdModel:
         vec = cond.get("vector") if isinstance(cond, dict) else None
         return self.apply_model_scaled(x_noisy.to(self.dtype_unet), t, ctx, vec)
 
-    def apply_model_scaled(self, x_in, t, context, vector=None):
+    def apply_model_scaled(self, x_in, t, context, vector=None, context_key: int = 0):
         dt = self.dtype_unet
         kwargs = {}
+        if context_key:
+            kwargs["context_key"] = context_key
         if vector is not None:
             kwargs["y"] = vector.to(dt)
         return self.unet.forward(x_in, t.to(dt), context.to(dt), **kwargs)

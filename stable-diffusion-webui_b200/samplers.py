@@ -166,6 +166,8 @@ class CFGDenoiser:
     {"crossattn": [B,T,C], "vector": [B,2816]}. `uncond`: list of prompt schedules or a tensor / dict likewise.
     InstructPix2Pix ("edit") checkpoints and inpainting `image_cond` are outside the accelerated path."""
 
+    _key_counter = 0  # context keys handed to the engine's cross-attention k|v cache (unique per process)
+
     def __init__(self, sampler):
         self.sampler = sampler
         self.model_wrap = None
@@ -185,6 +187,8 @@ class CFGDenoiser:
         self.last_noise_uncond = None
         self.opts = CFGDenoiserOptions()
         self._dev_cache = {}
+        self._ctx_keys = {}
+        self._ctx_refs = None
         self.on_cfg_denoiser = []   # callables(x, sigma_in, cond_in) -> None       (script_callbacks.on_cfg_denoiser)
         self.on_cfg_denoised = []   # callables(eps)                                (on_cfg_denoised)
         self.on_cfg_after_cfg = []  # callables(denoised) -> denoised | None        (on_cfg_after_cfg)
@@ -245,11 +249,31 @@ class CFGDenoiser:
             t = self._dev_cache[key] = build()
         return t
 
-    def _run_unet(self, x_in, t, cond_in):
+    def _run_unet(self, x_in, t, cond_in, key=0):
         sd = self.sampler.sd_model
         ctx = _cond_tensor(cond_in)
         vec = cond_in.get("vector") if isinstance(cond_in, dict) else None
-        return sd.apply_model_scaled(x_in, t, ctx, vec)  # engine UNet through the SdUnet seam
+        return sd.apply_model_scaled(x_in, t, ctx, vec, context_key=key)  # engine UNet through the SdUnet seam
+
+    def _context_key(self, cond, uncond, tag):
+        """A key that identifies the CONTENTS of the conditioning sent to the UNet this step: the cond / uncond objects of the
+        job (kept alive by sampler_extra_args), which scheduled prompts are active at this step, and which rows are sent."""
+        from . import prompt_parser
+
+        def active(c):
+            if isinstance(c, prompt_parser.MulticondLearnedConditioning):
+                return tuple(prompt_parser._active(cp.schedules, self.step) for prompts in c.batch for cp in prompts)
+            if isinstance(c, (list, tuple)):
+                return tuple(prompt_parser._active(sched, self.step) for sched in c)
+            return ()
+
+        ident = (id(cond), id(uncond), active(cond), active(uncond), tag)
+        key = self._ctx_keys.get(ident)
+        if key is None:
+            CFGDenoiser._key_counter += 1
+            key = self._ctx_keys[ident] = CFGDenoiser._key_counter
+            self._ctx_refs = (cond, uncond)  # the ids stay unique while the denoiser holds the objects
+        return key
 
     def forward(self, x, sigma, uncond, cond, cond_scale, s_min_uncond, image_cond):
         if state.interrupted or state.skipped:
@@ -260,6 +284,7 @@ class CFGDenoiser:
         sd = self.sampler.sd_model
         lib = L.load()
         opts = self.opts
+        cond_obj, uncond_obj = cond, uncond
         # ---- per-step conditioning (:168-169)
         if isinstance(cond, prompt_parser.MulticondLearnedConditioning):
             conds_list, tensor = prompt_parser.reconstruct_multicond_batch(cond, self.step)
@@ -311,8 +336,9 @@ class CFGDenoiser:
         # ---- UNet call(s) (:236-267)
         if _cond_tensor(tensor).shape[1] == _cond_tensor(uncond).shape[1] or skip_uncond:
             cond_in = tensor if skip_uncond else catenate_conds([tensor, uncond])
+            cacheable = not self.on_cfg_denoiser and not self.padded_cond_uncond and not self.padded_cond_uncond_v0
             if opts.batch_cond_uncond:
-                eps = self._run_unet(x_in, t, cond_in)
+                eps = self._run_unet(x_in, t, cond_in, self._context_key(cond_obj, uncond_obj, ("all", skip_uncond)) if cacheable else 0)
             else:
                 eps = torch.empty_like(x_in)
                 for a in range(0, rows, batch_size):

@@ -95,7 +95,9 @@ class SdxeUnet(_SdUnetBase):
         if self.engine is None:
             raise L.SdxeError("SdxeUnet.forward before activate()")
         y = kwargs.get("y", args[0] if args else None)
-        return self.engine.forward(x, timesteps, context, y)
+        # context_key: only the package's own CFGDenoiser passes one (it knows the conditioning is step-invariant);
+        # called from the stock webui the key is 0 and nothing is cached across calls
+        return self.engine.forward(x, timesteps, context, y, context_key=int(kwargs.get("context_key", 0)))
 
 
 class SdxeUnetOption(_SdUnetOptionBase):

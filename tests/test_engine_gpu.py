@@ -184,3 +184,36 @@ def test_plan_cache_lru_bounds_memory(cuda):
     print("pool bytes per cycle", sizes)
     assert sizes[2] <= sizes[1]
     eng.close()
+
+
+def test_cross_attention_kv_cache(cuda):
+    """sdxe_unet_set_context_key: with a key the k|v projection of the context is computed once per (plan, key) — same
+    output bits as without the key, fewer launches; a new key (or key 0) recomputes, so a changed context is honoured."""
+    from oracle.synth import init_module_
+    from oracle.unet import UNetModel, tiny_config
+    from sdwebui_b200 import lib as L
+    from sdwebui_b200.engine import UNetEngine, UNetSpec
+
+    cfg = tiny_config()
+    m = init_module_(UNetModel(cfg), 3).eval()
+    eng = UNetEngine(UNetSpec.from_any(cfg), dtype=torch.float16, device=cuda)
+    eng.load_state_dict({k: v.to(cuda) for k, v in m.state_dict().items()})
+    eng.finalize()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(2, 4, 16, 16, device=cuda, generator=g).half()
+    t = torch.tensor([900.0, 10.0], device=cuda).half()
+    c1 = torch.randn(2, 77, cfg.context_dim, device=cuda, generator=g).half()
+    c2 = torch.randn(2, 77, cfg.context_dim, device=cuda, generator=g).half()
+    lib = L.load()
+    base1, base2 = eng.forward(x, t, c1), eng.forward(x, t, c2)
+    assert not torch.equal(base1, base2)
+    n0 = lib.sdxe_launch_count()
+    a = eng.forward(x, t, c1, context_key=11)
+    n1 = lib.sdxe_launch_count()
+    b = eng.forward(x, t, c1, context_key=11)
+    n2 = lib.sdxe_launch_count()
+    assert torch.equal(a, base1) and torch.equal(b, base1)
+    assert (n2 - n1) < (n1 - n0), "the second call under the same key must skip the context projection"
+    assert torch.equal(eng.forward(x, t, c2, context_key=12), base2)      # new key -> new context is projected
+    assert torch.equal(eng.forward(x, t, c1, context_key=0), base1)       # key 0 -> always recomputed
+    eng.close()
