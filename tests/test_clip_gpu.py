@@ -91,11 +91,12 @@ def test_prompt_to_conditioning(cuda):
     cfg = CLIPTextConfig(vocab_size=3000, num_layers=3, id_start=2998, id_end=2999)
     torch.manual_seed(5)
     m = CLIPTextModel(cfg).eval().to(cuda)
+    with torch.no_grad():  # EmphasisOriginal divides by the chunk's mean: a freshly initialised final LayerNorm (bias 0) makes it ~0
+        m.text_model.final_layer_norm.bias.add_(0.3)
 
     def tok(texts, truncation=False, add_special_tokens=False):
         return {"input_ids": [[7 if w == "," else 10 + (sum((i + 1) * ord(c) for i, c in enumerate(w)) % 2900) for w in re.findall(r"[A-Za-z0-9]+|,", t)] for t in texts]}
 
-    tokenizer = types.SimpleNamespace(__call__=tok, get_vocab=lambda: {",</w>": 7}, bos_token_id=cfg.id_start, eos_token_id=cfg.id_end)
     tokenizer_callable = type("Tok", (), {"__call__": staticmethod(tok), "get_vocab": staticmethod(lambda: {",</w>": 7}),
                                           "bos_token_id": cfg.id_start, "eos_token_id": cfg.id_end})()
     for skip in (1, 2):
