@@ -49,6 +49,16 @@
 #ifndef ATT2_POLY_MASK
 #define ATT2_POLY_MASK 0x00
 #endif
+#ifndef ATT2_LAG
+#define ATT2_LAG 1
+#endif
+// The MUFU turn is handed to the other tile's warp after this many of the 16 groups of 8 exponentials (16 = at the end).
+// Half way (8) measured best: a lone warp sustains ~2/3 of the MUFU rate, so letting the second half of one row's
+// exponentials overlap the first half of the other tile's keeps the pipe fuller than strict alternation (L0 846 -> 790 us,
+// SDXL L1 550 -> 507 us; 4 / 6 / 7 / 9 / 10 / 12 are all worse: tools/gpu_scripts/attn_handover*.sh).
+#ifndef ATT2_HANDOVER
+#define ATT2_HANDOVER 8
+#endif
 
 namespace sdxe {
 
@@ -333,38 +343,41 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention2_kernel(const __gri
       if (trw) TR(t, i, 5);
 #endif
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      // 8 scores -> 4 packed registers, in place (r[4q..4q+3] <- r[8q..8q+7]). Software-pipelined by one group: the
-      // sums / packs of group q - 1 are issued after the 8 MUFU.EX2 of group q, so no instruction waits on a MUFU result
-      // that was issued just before it (ptxas keeps consumers next to producers otherwise: ~24 clk exposed per pair,
-      // 1550 clk per row instead of the 1024 the MUFU pipe needs).
-      float e[8];
+      // 8 scores -> 4 packed registers, in place (r[4q..4q+3] <- r[8q..8q+7]), software-pipelined:
+      // ATT2_LAG groups of 8 exponentials stay in flight: group q is issued (FFMA + MUFU.EX2), then group q - ATT2_LAG is
+      // consumed (row sums, 16-bit packing into r[4q'..4q'+3]).
+      float e[ATT2_LAG][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x = fmaf(__uint_as_float(r[j]), sl2, -mb);
-        e[j] = ((ATT2_POLY_MASK >> j) & 1) ? ex2_poly3(x) : ex2_approx(x);
-      }
+      for (int q = 0; q < 16 + ATT2_LAG; ++q) {
+        if (ATT2_HANDOVER < 16 && q == ATT2_HANDOVER) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mufu_turn(t ^ 1, quarter));
+        }
+        if (q >= ATT2_LAG) {
+          const int c = q - ATT2_LAG;
+          float* v = e[c % ATT2_LAG];
+          s0 += v[0] + v[1]; s1 += v[2] + v[3]; s2 += v[4] + v[5]; s3 += v[6] + v[7];
+          const uint32_t k0 = T::pack(v[0], v[1]), k1 = T::pack(v[2], v[3]), k2 = T::pack(v[4], v[5]), k3 = T::pack(v[6], v[7]);
+          if (q < 16) {
 #pragma unroll
-      for (int q = 1; q <= 16; ++q) {
-        float n[8];
-        if (q < 16) {
+            for (int j = 0; j < 8; ++j) {
+              const float x = fmaf(__uint_as_float(r[q * 8 + j]), sl2, -mb);
+              v[j] = ((ATT2_POLY_MASK >> j) & 1) ? ex2_poly3(x) : ex2_approx(x);
+            }
+          }
+          r[c * 4 + 0] = k0; r[c * 4 + 1] = k1; r[c * 4 + 2] = k2; r[c * 4 + 3] = k3;
+        } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float x = fmaf(__uint_as_float(r[q * 8 + j]), sl2, -mb);
-            n[j] = ((ATT2_POLY_MASK >> j) & 1) ? ex2_poly3(x) : ex2_approx(x);
+            e[q % ATT2_LAG][j] = ((ATT2_POLY_MASK >> j) & 1) ? ex2_poly3(x) : ex2_approx(x);
           }
         }
-        s0 += e[0] + e[1]; s1 += e[2] + e[3]; s2 += e[4] + e[5]; s3 += e[6] + e[7];
-        r[(q - 1) * 4 + 0] = T::pack(e[0], e[1]);
-        r[(q - 1) * 4 + 1] = T::pack(e[2], e[3]);
-        r[(q - 1) * 4 + 2] = T::pack(e[4], e[5]);
-        r[(q - 1) * 4 + 3] = T::pack(e[6], e[7]);
-        if (q < 16) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = n[j];
-        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(mufu_turn(t ^ 1, quarter));
+      if (ATT2_HANDOVER >= 16) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mufu_turn(t ^ 1, quarter));
+      }
       l_run += (s0 + s1) + (s2 + s3);
 #if SDXE_ATT_TRACE
       if (trw) TR(t, i, 3);
