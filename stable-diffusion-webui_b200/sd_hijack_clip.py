@@ -249,3 +249,72 @@ def open_clip_to_hf_state_dict(sd, prefix: str = "model."):
     if n == 0:
         raise L.SdxeError("no open_clip text tower under prefix " + repr(prefix))
     return out
+
+
+class FrozenOpenCLIPEmbedder2WithCustomWords(TextConditionalModel):
+    """SDXL's second text encoder (sgm FrozenOpenCLIPEmbedder2: OpenCLIP ViT-bigG text tower, layer="penultimate",
+    always_return_pooled) behind modules/sd_hijack_open_clip.py:38-71: z = the hidden state BEFORE the last block (no
+    ln_final), z.pooled = ln_final(last hidden state)[end-of-text position] @ text_projection.
+    `state_dict`: `conditioner.embedders.1.model.*` (open_clip names). The open_clip BPE tokenizer is injected
+    (`encode(text) -> ids`, `encoder` dict); pad id is 0, not end-of-text (:45)."""
+
+    def __init__(self, state_dict, tokenizer, num_heads: int = 20, dtype=torch.float16, device="cuda:0", opts: Optional[TextOptions] = None,
+                 prefix: str = "model.", layer: str = "penultimate"):
+        super().__init__(opts)
+        self.tokenizer = tokenizer
+        hf = open_clip_to_hf_state_dict(state_dict, prefix)
+        self.spec = CLIPTextSpec.from_state_dict(hf, num_heads=num_heads, act="gelu")
+        self.engine = CLIPTextEngine(self.spec, dtype=dtype, device=device)
+        self.engine.load_state_dict(hf)
+        self.engine.finalize()
+        proj = state_dict[prefix + "text_projection"]                    # [width, embed_dim], used as x @ proj
+        self.text_projection_t = proj.t().contiguous().to(device=device, dtype=dtype)  # [embed_dim, width] for out = A W^T
+        self.layer = layer
+        self.return_pooled = True
+        self.comma_token = tokenizer.encoder.get(",</w>")
+        self.id_start = tokenizer.encoder["<start_of_text>"]
+        self.id_end = tokenizer.encoder["<end_of_text>"]
+        self.id_pad = 0
+
+    def tokenize(self, texts):
+        return [self.tokenizer.encode(text) for text in texts]
+
+    def encode_with_transformers(self, tokens):
+        from . import ops
+
+        n = self.spec.num_layers
+        z = self.engine.forward(tokens, layer=n - 1 if self.layer == "penultimate" else n, final_norm=self.layer != "penultimate")
+        last = z if self.layer != "penultimate" else self.engine.forward(tokens, layer=n, final_norm=True)
+        eot = tokens.to(last.device).argmax(dim=-1)                      # open_clip pools at the highest token id = <end_of_text>
+        rows = last[torch.arange(last.shape[0], device=last.device), eot].contiguous()
+        pooled = ops.gemm(rows, self.text_projection_t)                  # tcgen05 GEMM, M = number of prompts
+        z.pooled = pooled  # the reference attaches the attribute to the hidden-state tensor (sd_hijack_open_clip.py:60-64)
+        return z
+
+    def close(self):
+        self.engine.close()
+
+
+def sdxl_size_embedding(values: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    """sgm ConcatTimestepEmbedderND(outdim=256): every scalar of `values` [B, k] -> sinusoidal embedding (cos | sin, the
+    timestep_embedding of modules/sd_hijack_unet.py:58-78), concatenated -> [B, k * dim]."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=values.device) / half)
+    args = values.reshape(-1)[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    return emb.reshape(values.shape[0], -1)
+
+
+def sdxl_get_learned_conditioning(clip_l, clip_g, texts, width=1024, height=1024, crop_top=0, crop_left=0, is_negative_prompt=False):
+    """modules/sd_models_xl.py:12-34 + sgm GeneralConditioner for SDXL-base: crossattn = CLIP-L hidden[11] | bigG penultimate
+    (768 + 1280), vector = pooled (1280) | original size | crop | target size (3 x 2 x 256) = 2816. An all-empty negative
+    prompt is zeroed (force_zero_embeddings=['txt'])."""
+    zl = clip_l(texts)
+    zg, pooled = clip_g(texts)
+    if is_negative_prompt and all(x == "" for x in texts):
+        zl, zg, pooled = torch.zeros_like(zl), torch.zeros_like(zg), torch.zeros_like(pooled)
+    dev, B = zl.device, len(texts)
+    size = torch.tensor([[height, width]], device=dev).repeat(B, 1)
+    crop = torch.tensor([[crop_top, crop_left]], device=dev).repeat(B, 1)
+    vec = torch.cat([pooled.float(), sdxl_size_embedding(size), sdxl_size_embedding(crop), sdxl_size_embedding(size)], dim=1)
+    return {"crossattn": torch.cat([zl, zg.to(zl.dtype)], dim=-1), "vector": vec.to(zl.dtype)}

@@ -127,3 +127,69 @@ def test_prompt_to_conditioning(cuda):
         want = m.hidden_states(ids)[2]
     assert rel_err(z, want) < 4e-3
     xl.close()
+
+
+def test_open_clip2_pooled_and_sdxl_conditioning(cuda):
+    """FrozenOpenCLIPEmbedder2WithCustomWords on an open_clip-named state dict (small bigG-like tower: GELU, fused in_proj,
+    text_projection): penultimate hidden state without ln_final + pooled = ln_final(last)[eot] @ text_projection, against the
+    torch restatement; then the SDXL {"crossattn", "vector"} assembly (modules/sd_models_xl.py:12-34) shapes."""
+    import types
+
+    from oracle.clip import CLIPTextConfig, CLIPTextModel
+    from sdwebui_b200.sd_hijack_clip import (FrozenCLIPEmbedderForSDXLWithCustomWords, FrozenOpenCLIPEmbedder2WithCustomWords,
+                                             sdxl_get_learned_conditioning)
+
+    C, Lr, Hh = 256, 4, 4
+    cfg = CLIPTextConfig(vocab_size=3000, hidden_size=C, intermediate_size=4 * C, num_layers=Lr, num_heads=Hh, id_start=2998, id_end=2999)
+    torch.manual_seed(7)
+    m = CLIPTextModel(cfg).eval()
+    for layer in m.text_model.encoder.layers:
+        mlp = layer.mlp
+        mlp.forward = (lambda x, mlp=mlp: mlp.fc2(torch.nn.functional.gelu(mlp.fc1(x))))
+    with torch.no_grad():
+        m.text_model.final_layer_norm.bias.add_(0.2)
+    m = m.to(cuda)
+    hf = m.state_dict()
+    oc = {"model.token_embedding.weight": hf["text_model.embeddings.token_embedding.weight"],
+          "model.positional_embedding": hf["text_model.embeddings.position_embedding.weight"],
+          "model.ln_final.weight": hf["text_model.final_layer_norm.weight"], "model.ln_final.bias": hf["text_model.final_layer_norm.bias"],
+          "model.text_projection": torch.randn(C, 320, generator=torch.Generator().manual_seed(3)).to(cuda) * C ** -0.5}
+    for n in range(Lr):
+        s_, d_ = f"text_model.encoder.layers.{n}.", f"model.transformer.resblocks.{n}."
+        oc[d_ + "attn.in_proj_weight"] = torch.cat([hf[s_ + f"self_attn.{k}_proj.weight"] for k in "qkv"])
+        oc[d_ + "attn.in_proj_bias"] = torch.cat([hf[s_ + f"self_attn.{k}_proj.bias"] for k in "qkv"])
+        for a, b in (("self_attn.out_proj", "attn.out_proj"), ("layer_norm1", "ln_1"), ("layer_norm2", "ln_2"), ("mlp.fc1", "mlp.c_fc"), ("mlp.fc2", "mlp.c_proj")):
+            oc[d_ + b + ".weight"], oc[d_ + b + ".bias"] = hf[s_ + a + ".weight"], hf[s_ + a + ".bias"]
+
+    def enc(text):
+        return [10 + (sum((i + 1) * ord(c) for i, c in enumerate(w)) % 2900) for w in re.findall(r"[A-Za-z0-9]+", text)]
+
+    tok = types.SimpleNamespace(encode=enc, encoder={",</w>": 7, "<start_of_text>": cfg.id_start, "<end_of_text>": cfg.id_end})
+    g = FrozenOpenCLIPEmbedder2WithCustomWords(oc, tok, num_heads=Hh, dtype=torch.float16, device=cuda)
+    texts = ["a castle on a hill", "portrait"]
+    z, pooled = g.forward(texts)
+    assert z.shape == (2, 77, C) and pooled.shape == (2, 320)
+    chunks = [g.tokenize_line(t)[0][0] for t in texts]
+    ids = torch.tensor([c.tokens for c in chunks], device=cuda)
+    for b, c in enumerate(chunks):  # pad id 0 after end-of-text, as process_tokens does for open_clip
+        ids[b, c.tokens.index(cfg.id_end) + 1:] = 0
+    with torch.no_grad():
+        hs = m.hidden_states(ids)
+        want_z = hs[-2]
+        last = m.text_model.final_layer_norm(hs[-1])
+        want_p = last[torch.arange(2), ids.argmax(-1)] @ oc["model.text_projection"]
+    ez, ep = rel_err(z, want_z), rel_err(pooled, want_p)
+    print(f"open_clip2: penultimate rel err {ez:.3e}, pooled rel err {ep:.3e}")
+    assert ez < 4e-3 and ep < 6e-3
+    # SDXL assembly with a CLIP-L-like partner (hidden[layer_idx], no final norm)
+    cfg_l = CLIPTextConfig(vocab_size=3000, hidden_size=128, intermediate_size=512, num_layers=3, num_heads=2, id_start=2998, id_end=2999)
+    ml = CLIPTextModel(cfg_l).eval().to(cuda)
+    tok_l = type("Tok", (), {"__call__": staticmethod(lambda texts, truncation=False, add_special_tokens=False: {"input_ids": [enc(t) for t in texts]}),
+                             "get_vocab": staticmethod(lambda: {",</w>": 7}), "bos_token_id": cfg_l.id_start, "eos_token_id": cfg_l.id_end})()
+    l = FrozenCLIPEmbedderForSDXLWithCustomWords(ml.state_dict(), tok_l, dtype=torch.float16, device=cuda, layer="hidden", layer_idx=2)
+    c = sdxl_get_learned_conditioning(l, g, texts, width=1024, height=768)
+    assert c["crossattn"].shape == (2, 77, 128 + C) and c["vector"].shape == (2, 320 + 6 * 256)
+    uc = sdxl_get_learned_conditioning(l, g, ["", ""], is_negative_prompt=True)
+    assert float(uc["crossattn"].abs().max()) == 0.0 and float(uc["vector"][:, :320].abs().max()) == 0.0
+    g.close()
+    l.close()
