@@ -17,7 +17,7 @@ dev = torch.device("cuda:0")
 w = bench.WORKLOADS[args.config]
 dt = torch.bfloat16
 B = w["batch"]
-model, _ = bench.build_model(args.config, dt, dev, 0, 1)
+model, _ = bench.build_model(w["arch"], dt, dev, 0, 1)
 c, u = bench.make_conds(w, B, dev, 7)
 c, u = bench.to_dev(c, dev, False), bench.to_dev(u, dev, False)
 seeds = list(range(1000, 1000 + B))
