@@ -40,6 +40,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 # algorithmic work (BASELINE.md §2 / SURVEY §8(d)): 2*MAC over conv / linear / QK^T / PV, no padding, no recompute
+PREROLL_S = float(os.environ.get("SDXE_BENCH_PREROLL_S", "6"))  # untimed load before the timed regions (see measure_workload)
 TFLOP = {
     "sd15": {"unet_sample": 0.8033, "vae": 2.515, "per_image": 34.65},
     "sdxl": {"unet_sample": 6.761, "vae": 10.47, "per_image": 416.1},
@@ -354,6 +355,15 @@ def measure_workload(key, dtype_name, rank, world, local, device, steps, warmup,
     for _ in range(warmup):
         step_resident()
     step_e2e()
+    # untimed pre-roll: under the 1 kW power cap the SM clock settles ~4-5 % below its cold value over the first seconds
+    # of load; without it the first timed region (`value`) runs on a colder GPU than the second (`e2e`) and the two differ
+    # by drift, not by the host copies (interleaved A/B: 393.1 vs 395.7 ms per batch, tools/profile_pipeline.py)
+    torch.cuda.synchronize()
+    t_roll, n_roll = time.perf_counter(), 0
+    while time.perf_counter() - t_roll < PREROLL_S:
+        step_resident()
+        torch.cuda.synchronize()
+        n_roll += 1
     if clock_sampler is not None:
         clock_sampler.start()
     ms_res, launches = timed(step_resident, steps)
@@ -382,7 +392,8 @@ def measure_workload(key, dtype_name, rank, world, local, device, steps, warmup,
                  "ms_per_step": ms_res / steps, "dtype": dtype_name,
                  "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world} (image shards, no per-step collective)",
                             "l2": "working set (>= 1.7 GB weights + activations) >> 126 MB L2: no explicit flush",
-                            "weights": "random-init, exact architecture", "weight_broadcast_bytes": bcast_bytes},
+                            "weights": "random-init, exact architecture", "weight_broadcast_bytes": bcast_bytes,
+                            "preroll": f"{n_roll} untimed steps (>= {PREROLL_S:.0f} s of load) after the {warmup} warm-ups: both timed regions at settled clocks"},
                  "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": nbytes(c_host) + nbytes(u_host),
                          "d2h_bytes_per_step": B * w["height"] * w["width"] * 3 * (4 if w["hires"] else 1), "ms_per_step": ms_e2e / steps},
                  "gpu_launches": int(launches), "clocks": clocks,

@@ -367,6 +367,27 @@ SDXE_DEVINL float silu_f(float x) { return x * rcp_approx(1.f + ex2_approx(-1.44
 SDXE_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 // erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below 16-bit output resolution):
 // one MUFU.EX2, one MUFU.RCP and a handful of FMAs instead of libdevice erff's branchy ~30 instructions.
+// With erf(|z|) = 1 - P(t) e^{-z^2}, t = 1 / (1 + p |z|), z = x / sqrt 2:
+//   gelu(x) = x/2 (1 + erf z) = max(x, 0) - |x|/2 P(t) e^{-z^2}        (both signs of x)
+// and with u = x sqrt(log2(e) / 2) (so that e^{-z^2} = 2^{-u^2}) the constants |z| / |u| and |x| / (2 |u|) fold into p and
+// into P's coefficients: 11 FP32-pipe instructions + 2 MUFU per element (the textbook arrangement below took 15 + 2, and
+// the GEGLU epilogue is instruction-bound: profiles/r1_notes.md finding 3).
+#ifndef SDXE_GELU_V1
+SDXE_DEVINL float gelu_fast_f(float x) {
+  constexpr float C = 0.84932180028801904f;        // sqrt(log2(e) / 2)
+  constexpr float S = 0.83255461115769776f;        // |z| / |u| = 1 / sqrt(log2(e))
+  constexpr float H = 0.58870501125773735f;        // |x| / (2 |u|) = 1 / (2 C)
+  const float u = x * C;
+  const float a = fabsf(u);
+  const float t = rcp_approx(fmaf(0.3275911f * S, a, 1.f));
+  float p = fmaf(1.061405429f * H, t, -1.453152027f * H);
+  p = fmaf(p, t, 1.421413741f * H);
+  p = fmaf(p, t, -0.284496736f * H);
+  p = fmaf(p, t, 0.254829592f * H);
+  const float e = ex2_approx(-u * u);
+  return fmaf(-(a * e), p * t, fmaxf(x, 0.f));
+}
+#else
 SDXE_DEVINL float gelu_fast_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
@@ -379,6 +400,7 @@ SDXE_DEVINL float gelu_fast_f(float x) {
   const float erfv = copysignf(erf_abs, x);
   return 0.5f * x * (1.f + erfv);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host: error handling + tensor-map encoding through the driver entry point (no -lcuda link)

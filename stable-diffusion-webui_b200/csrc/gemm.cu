@@ -31,16 +31,24 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+// GEGLU variants: 16 epilogue warps (four per lane quarter). Their epilogue is instruction-bound — ~24 issue slots per
+// output element (two accumulators, bias / LayerNorm fold on both, erf-GELU with two MUFU ops) — and with eight warps
+// only two were resident per scheduler: issue slots 53 % used, 6.2 k cycles per 128 x 256 tile against 2.5 k of tensor
+// work at K = 320 (profiles/r2_ncu_geglu.txt). Blocks above 512 threads are held to 96 registers, so these warps work
+// in 16-column chunks (32 live accumulator registers instead of 64).
+static constexpr int GEGLU_EPI_WARPS = 16;
+static constexpr int GEGLU_THREADS = 64 + 32 * GEGLU_EPI_WARPS;
+static constexpr int GEGLU_CHUNK_BYTES = 32 * 16 * 2;  // 32 rows x 16 columns, 16 bit (same staging bytes per CTA as 8 x 2 KB)
 static constexpr int TMEM_COLS = 512;
 static constexpr int SBIAS_BYTES = 4 * 256 * 4;  // per-tile bias and LayerNorm-fold c1 slices in smem, double buffered
 static constexpr int CHUNK_BYTES = 32 * 32 * 2;   // one epilogue chunk: 32 rows x 32 columns, 16 bit
 static constexpr int NUM_EPI_WARPS = 8;
-static constexpr int NUM_BARS_FIXED = 4 + 3 * NUM_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][<= 3 buffers]
+static constexpr int NUM_BARS_FIXED = 4 + 3 * GEGLU_EPI_WARPS;  // tfull[2], tempty[2], residual-landed[warp][<= 3 buffers]
 
 // EPI / RES / ROWVEC are compile-time so that the epilogue's inner loop carries no mode branches (it was spending
 // two thirds of its instructions on flag tests and parameter reloads, and the epilogue bounds every small-K GEMM).
 template <bool BF16, int EPI, bool RES, bool ROWVEC, bool CLUSTER, bool LNF, bool STAT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
+__global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs a) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -94,7 +102,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), clustered ? 16 : 8);  // paired: both CTAs' epilogue warps free the leader's accumulator
+      // every epilogue warp frees the accumulator (paired: both CTAs' warps free the leader's)
+      mbar_init(tempty_bar(i), (EPI == EPI_GEGLU ? GEGLU_EPI_WARPS : NUM_EPI_WARPS) * (clustered ? 2 : 1));
     }
     if (RES)
       for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); mbar_init(res_bar(w, 2), 1); }
@@ -221,6 +230,123 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if constexpr (EPI == EPI_GEGLU) {
+    // ------------------------------------------------------------------ epilogue warps, GEGLU: out = value * gelu(gate)
+    // Sixteen warps: warp w may touch TMEM lanes 32 (w % 4) .. +31, the four warps of a lane quarter take every fourth
+    // 16-column chunk. Value and gate accumulators of a chunk are read together (columns c and BN / 2 + c), the product
+    // is staged in a 32B-swizzled 1 KB buffer and leaves through a TMA store (same path as the plain epilogue below).
+    const int quarter = warp & 3;
+    const int ew = warp - 2;             // 0..15
+    const int esub = ew >> 2;            // 0..3
+    const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t tile_ctr = 0;
+    const int half = BN >> 1;            // output columns per tile; the gate accumulators start at column `half`
+    const float* const biasp = a.bias;
+    const int M = a.M;
+    const uint32_t my_buf = stage_buf_base + (uint32_t)(ew * NBUF) * GEGLU_CHUNK_BYTES;
+    uint32_t chunk_ctr = 0;
+    for (int tile = work_first; tile < num_tiles; tile += work_step, ++tile_ctr) {
+      const int n_blk = tile % num_n;
+      const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
+      const int m = m_blk * BLOCK_M + row;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int n_out0 = n_blk * half;
+      float* sb = sbias + (tile_ctr & 1u) * 256;
+      float* sc = sbias + 512 + (tile_ctr & 1u) * 256;
+      for (int j = et; j < BN; j += 32 * GEGLU_EPI_WARPS) {
+        // PACK_GEGLU weights / bias / c1: tile n_blk's rows are [half value rows | the matching half gate rows]; N % BN == 0
+        sb[j] = biasp != nullptr ? __ldg(biasp + n_blk * BN + j) : 0.f;
+        if (LNF) sc[j] = __ldg(a.c1 + n_blk * BN + j);
+      }
+      float ln_mu = 0.f, ln_rs = 1.f;
+      if (LNF) {
+        float ps = 0.f, pq = 0.f;
+        if (m < M) {
+          for (int pp = 0; pp < a.ln_parts; ++pp) {
+            const float2 t = __ldg(a.ln_part + (size_t)pp * M + m);
+            ps += t.x;
+            pq += t.y;
+          }
+        }
+        ln_mu = ps * a.ln_inv_c;
+        ln_rs = rsqrtf(fmaxf(pq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * GEGLU_EPI_WARPS) : "memory");  // bias of this tile visible to all epilogue warps
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = esub * 16; c0 < half; c0 += 64, ++chunk_ctr) {
+        const uint32_t buf = my_buf + (chunk_ctr % (uint32_t)NBUF) * GEGLU_CHUNK_BYTES;
+        uint32_t r[16], rg[16];
+        tmem_ld16(t_row + c0, r);
+        tmem_ld16(t_row + half + c0, rg);
+        tc_wait_ld();
+        uint4 packed[2];
+#pragma unroll
+        for (int g = 0; g < 16; g += 8) {
+          float v[8], gt[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = __uint_as_float(r[g + j]); gt[j] = __uint_as_float(rg[g + j]); }
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + c0 + g + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(sb + half + c0 + g), d1 = *reinterpret_cast<const float4*>(sb + half + c0 + g + 4);
+          if (LNF) {
+            const float4 k0 = *reinterpret_cast<const float4*>(sc + c0 + g), k1 = *reinterpret_cast<const float4*>(sc + c0 + g + 4);
+            const float4 q0 = *reinterpret_cast<const float4*>(sc + half + c0 + g), q1 = *reinterpret_cast<const float4*>(sc + half + c0 + g + 4);
+            v[0] = fmaf(ln_rs, v[0] - ln_mu * k0.x, b0.x); v[1] = fmaf(ln_rs, v[1] - ln_mu * k0.y, b0.y);
+            v[2] = fmaf(ln_rs, v[2] - ln_mu * k0.z, b0.z); v[3] = fmaf(ln_rs, v[3] - ln_mu * k0.w, b0.w);
+            v[4] = fmaf(ln_rs, v[4] - ln_mu * k1.x, b1.x); v[5] = fmaf(ln_rs, v[5] - ln_mu * k1.y, b1.y);
+            v[6] = fmaf(ln_rs, v[6] - ln_mu * k1.z, b1.z); v[7] = fmaf(ln_rs, v[7] - ln_mu * k1.w, b1.w);
+            gt[0] = fmaf(ln_rs, gt[0] - ln_mu * q0.x, d0.x); gt[1] = fmaf(ln_rs, gt[1] - ln_mu * q0.y, d0.y);
+            gt[2] = fmaf(ln_rs, gt[2] - ln_mu * q0.z, d0.z); gt[3] = fmaf(ln_rs, gt[3] - ln_mu * q0.w, d0.w);
+            gt[4] = fmaf(ln_rs, gt[4] - ln_mu * q1.x, d1.x); gt[5] = fmaf(ln_rs, gt[5] - ln_mu * q1.y, d1.y);
+            gt[6] = fmaf(ln_rs, gt[6] - ln_mu * q1.z, d1.z); gt[7] = fmaf(ln_rs, gt[7] - ln_mu * q1.w, d1.w);
+          } else {
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            gt[0] += d0.x; gt[1] += d0.y; gt[2] += d0.z; gt[3] += d0.w;
+            gt[4] += d1.x; gt[5] += d1.y; gt[6] += d1.z; gt[7] += d1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_fast_f(gt[j]);
+          packed[g >> 3].x = T16<BF16>::pack(v[0], v[1]);
+          packed[g >> 3].y = T16<BF16>::pack(v[2], v[3]);
+          packed[g >> 3].z = T16<BF16>::pack(v[4], v[5]);
+          packed[g >> 3].w = T16<BF16>::pack(v[6], v[7]);
+        }
+        // the buffer was last read by the store of chunk c - NBUF: that read must be over before it is overwritten
+        if (elect_one()) { if (deep) bulk_wait_read_1(); else bulk_wait_read_all(); }
+        __syncwarp();
+        const uint32_t lin0 = (uint32_t)lane * 32u;  // 32-byte rows, 32B swizzle: 16-byte unit index ^= address bit 7
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t lin = lin0 + (uint32_t)(g * 16);
+          const uint4 u = packed[g];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(buf + (lin ^ (((lin >> 7) & 1u) << 4))), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&a.tmO16, buf, n_out0 + c0, row0);
+          bulk_commit_group();
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (clustered && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
+        else mbar_arrive(tempty_bar(acc));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (elect_one()) bulk_wait_all();
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps
     // Row-per-thread (the only way tcgen05.ld hands out data): a thread owns 64 contiguous bytes of one output row per
@@ -237,9 +363,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     uint32_t acc_phase = 0;
     uint32_t tile_ctr = 0;
     uint32_t chunk_ctr = 0;              // chunks this warp has handled: staging buffer / barrier parity
-    constexpr bool GEGLU = EPI == EPI_GEGLU;
-    const int out_cols = GEGLU ? (BN >> 1) : BN;  // output columns produced per tile
-    const int half = BN >> 1;
+    const int out_cols = BN;             // output columns produced per tile
     const float* const biasp = a.bias;
     const int M = a.M, N = a.N;
     const uint32_t my_buf = stage_buf_base + (uint32_t)(ew * NBUF) * CHUNK_BYTES;
@@ -298,13 +422,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         const uint32_t b = chunk_ctr % (uint32_t)NBUF;
         const uint32_t buf = my_buf + b * CHUNK_BYTES;
         uint32_t r[32];
-        uint32_t rg[GEGLU ? 32 : 1];
         if (nc == 32) tmem_ld32(t_row + c0, r);
         else tmem_ld16(t_row + c0, r);
-        if (GEGLU) {
-          if (nc == 32) tmem_ld32(t_row + half + c0, rg);
-          else tmem_ld16(t_row + half + c0, rg);
-        }
         if (RES) {
           // the other buffer is free once the previous chunk's store has read it: fetch the next residual chunk into it
           if (elect_one()) {
@@ -337,24 +456,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                 v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                 v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
               }
-            }
-            if (GEGLU) {
-              const float4 b0 = *reinterpret_cast<const float4*>(sb + half + c0 + g), b1 = *reinterpret_cast<const float4*>(sb + half + c0 + g + 4);
-              float gt[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(rg[(GEGLU ? g : 0) + (GEGLU ? j : 0)]);
-              if (LNF) {
-                const float4 k0 = *reinterpret_cast<const float4*>(sc + half + c0 + g), k1 = *reinterpret_cast<const float4*>(sc + half + c0 + g + 4);
-                gt[0] = fmaf(ln_rs, gt[0] - ln_mu * k0.x, b0.x); gt[1] = fmaf(ln_rs, gt[1] - ln_mu * k0.y, b0.y);
-                gt[2] = fmaf(ln_rs, gt[2] - ln_mu * k0.z, b0.z); gt[3] = fmaf(ln_rs, gt[3] - ln_mu * k0.w, b0.w);
-                gt[4] = fmaf(ln_rs, gt[4] - ln_mu * k1.x, b1.x); gt[5] = fmaf(ln_rs, gt[5] - ln_mu * k1.y, b1.y);
-                gt[6] = fmaf(ln_rs, gt[6] - ln_mu * k1.z, b1.z); gt[7] = fmaf(ln_rs, gt[7] - ln_mu * k1.w, b1.w);
-              } else {
-              gt[0] += b0.x; gt[1] += b0.y; gt[2] += b0.z; gt[3] += b0.w;
-              gt[4] += b1.x; gt[5] += b1.y; gt[6] += b1.z; gt[7] += b1.w;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= gelu_fast_f(gt[j]);
             }
             if (ROWVEC) {
               if (rv) {
@@ -581,11 +682,12 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
     kern = gemm_variant(20 + (bf16 ? 4 : 0) + xi);
   }
   if (gemm_init() != 0) return -1;
+  const int threads = a.epi == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREADS;
   if (a.cluster == 2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -599,7 +701,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SDXE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
   } else {
-    SDXE_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, a));
+    SDXE_CUDA_CHECK(launch_k(kern, dim3(grid), dim3(threads), smem, stream, a));
   }
   SDXE_CUDA_CHECK(cudaGetLastError());
   return 0;

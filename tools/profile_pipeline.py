@@ -58,7 +58,29 @@ def timeit(fn, k):
     return e0.elapsed_time(e1) / k
 
 
+def full_e2e():
+    ch, uh = bench.to_dev(c_host, dev), bench.to_dev(u_host, dev)
+    p = StableDiffusionProcessingTxt2Img(sd_model=model, c=ch, uc=uh, seeds=seeds, sampler_name=w["sampler"], steps=w["steps"],
+                                         cfg_scale=7.0, width=w["width"], height=w["height"], randn_source="GPU")
+    return process_images(p, to_host=True)
+
+
+c_host, u_host = bench.make_conds(w, B, dev, 7)
+c_host, u_host = bench.pin(c_host), bench.pin(u_host)
 full()
 full()
+full_e2e()
+# resident vs host-buffer call, interleaved so that clock drift under the power cap hits both alike
+import time  # noqa: E402
+ab = {"resident": [], "e2e": []}
+for _ in range(args.iters):
+    for name, fn in (("resident", full), ("e2e", full_e2e)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ab[name].append((time.perf_counter() - t0) * 1e3)
+print(f"{args.config}: interleaved wall clock per batch: resident {sorted(ab['resident'])[len(ab['resident']) // 2]:.1f} ms, "
+      f"e2e {sorted(ab['e2e'])[len(ab['e2e']) // 2]:.1f} ms  (all: {[round(v, 1) for v in ab['resident']]} vs {[round(v, 1) for v in ab['e2e']]})")
 tf, tu, tv = timeit(full, args.iters), timeit(unet_only, args.iters), timeit(vae_only, args.iters)
 print(f"{args.config}: process_images {tf:.1f} ms = {w['steps']} UNet calls {tu:.1f} ms + VAE decode {tv:.1f} ms + sampler/glue {tf - tu - tv:.1f} ms")
