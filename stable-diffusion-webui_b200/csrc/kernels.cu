@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(512) gn_onepass_kernel(const uint32_t* __restr
   }
 }
 
+static int skinny_linear_init();
 int kernels_init() {
   static bool done = false;
   if (!done) {
@@ -245,6 +246,7 @@ int kernels_init() {
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SDXE_CUDA_CHECK(cudaFuncSetAttribute(gn_onepass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (skinny_linear_init() != 0) return -1;
     done = true;
   }
   return 0;
@@ -606,73 +608,99 @@ int timestep_embedding_launch(const void* t, int t_dtype, float* out, int m, int
   return 0;
 }
 
-// Each warp produces NPW output features for all M rows; lanes split K in 16-byte weight vectors.
-template <bool BF16, int MT, int NPW>
-__global__ void skinny_linear_kernel(const float* __restrict__ in, int ldi, const uint4* __restrict__ W,
-                                     const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ out,
-                                     int ldo, int M, int N, int K, int silu_out) {
+// Skinny linear (a handful of rows against a wide weight matrix: time_embed, label_emb, all emb_layers in one launch):
+// out[M <= 16 per pass, N] = in[M, K] (fp32 holding 16-bit values) x W[N, K]^T. Sixteen rows are exactly one m16n8k16
+// warp-MMA tile — far below tcgen05's 64-row minimum, so this one op uses mma.sync: the kernel only has to stream the
+// weight matrix once at HBM speed. A block stages its 16 input rows in shared memory as 16-bit (lossless: every producer
+// rounds to the model dtype); each warp owns 8 output features; per 32 k a lane reads ONE 16-byte weight vector (its
+// feature gid, k = 32 s + 8 tig .. + 7) and two 16-byte activation vectors (rows gid, gid + 8, same k) and issues two
+// MMAs — the k index inside a 32-block is permuted identically for both operands, which a dot product does not see.
+// (History: FMA versions of this op ran the 16 x 20480 x 1280 emb_layers product at 112 us and 66 us.)
+constexpr int SKL_WARPS = 8;
+template <bool BF16>
+SDXE_DEVINL void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  if (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <bool BF16>
+__global__ void __launch_bounds__(SKL_WARPS * 32)
+skinny_linear_kernel(const float* __restrict__ in, int ldi, const uint4* __restrict__ W, const float* __restrict__ b,
+                     const float* add, float* out, int ldo, int M, int N, int K, int silu_out) {
   pdl_launch_dependents();
   pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int n0 = warp * NPW;
-  if (n0 >= N) return;
+  extern __shared__ __align__(16) uint8_t skl_in[];  // [16][row_bytes] 16-bit activations, K zero-padded to a multiple of 32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int n0 = (blockIdx.x * SKL_WARPS + warp) * 8;
+  const int Kp = (K + 31) & ~31;
+  const int row_bytes = ((Kp * 2 + 127) & ~127) + 64;  // = 64 mod 128: the 8 lanes of an LDS.128 phase (2 rows x 4 pieces) hit 8 distinct 16-byte bank groups
   const int KV = K >> 3;
-  for (int m0 = 0; m0 < M; m0 += MT) {
-    float acc[NPW][MT];
-#pragma unroll
-    for (int i = 0; i < NPW; ++i)
-#pragma unroll
-      for (int r = 0; r < MT; ++r) acc[i][r] = 0.f;
-    for (int kv = lane; kv < KV; kv += 32) {
-      float w[NPW][8];
-#pragma unroll
-      for (int i = 0; i < NPW; ++i) {
-        if (n0 + i < N) unpack8<BF16>(__ldg(W + (size_t)(n0 + i) * KV + kv), w[i]);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[i][j] = 0.f;
-        }
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    __syncthreads();  // the previous row tile is no longer read
+    for (int idx = threadIdx.x; idx < 16 * (Kp >> 2); idx += blockDim.x) {
+      const int r = idx / (Kp >> 2), c = idx - r * (Kp >> 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && c * 4 < K) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi) + c);
+      uint2 u;
+      u.x = T16<BF16>::pack(v.x, v.y);
+      u.y = T16<BF16>::pack(v.z, v.w);
+      *reinterpret_cast<uint2*>(skl_in + (size_t)r * row_bytes + c * 8) = u;
+    }
+    __syncthreads();
+    if (n0 < N) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool col_ok = n0 + gid < N;
+      const uint4* wrow = W + (size_t)(col_ok ? n0 + gid : n0) * KV;
+      const uint8_t* a_lo = skl_in + (size_t)gid * row_bytes + tig * 16;
+      const uint8_t* a_hi = a_lo + 8 * (size_t)row_bytes;
+      const int steps = Kp >> 5;
+#pragma unroll 4
+      for (int s = 0; s < steps; ++s) {
+        const int kv = s * 4 + tig;  // this lane's 16-byte weight vector (8 k) of the 32-k block
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (kv < KV) w = __ldg(wrow + kv);
+        const uint4 lo = *reinterpret_cast<const uint4*>(a_lo + s * 64);
+        const uint4 hi = *reinterpret_cast<const uint4*>(a_hi + s * 64);
+        mma_16816<BF16>(acc, lo.x, hi.x, lo.y, hi.y, w.x, w.y);
+        mma_16816<BF16>(acc, lo.z, hi.z, lo.w, hi.w, w.z, w.w);
       }
+      // c0, c1: (row gid, features n0 + 2 tig, + 1); c2, c3: row gid + 8
 #pragma unroll
-      for (int r = 0; r < MT; ++r) {
-        if (m0 + r < M) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(in + (size_t)(m0 + r) * ldi + kv * 8 + 4));
-          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int i = 0; i < NPW; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][r] = fmaf(a[j], w[i][j], acc[i][r]);
+      for (int q = 0; q < 4; ++q) {
+        const int r = m0 + gid + (q >> 1) * 8, n = n0 + tig * 2 + (q & 1);
+        if (r < M && n < N) {
+          float v = round16<BF16>(acc[q] + (b ? __ldg(b + n) : 0.f));
+          if (add) v = round16<BF16>(v + add[(size_t)r * ldo + n]);
+          if (silu_out) v = round16<BF16>(silu_f(v));  // the only consumer applies SiLU first (emb_layers / time_embed)
+          out[(size_t)r * ldo + n] = v;
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < NPW; ++i)
-#pragma unroll
-      for (int r = 0; r < MT; ++r) {
-        float v = acc[i][r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && n0 + i < N && m0 + r < M) {
-          v = round16<BF16>(v + (b ? __ldg(b + n0 + i) : 0.f));
-          if (add) v = round16<BF16>(v + add[(size_t)(m0 + r) * ldo + n0 + i]);
-          if (silu_out) v = round16<BF16>(silu_f(v));  // the only consumer applies SiLU first (emb_layers / time_embed)
-          out[(size_t)(m0 + r) * ldo + n0 + i] = v;
-        }
-      }
   }
+}
+
+static int skinny_linear_init() {
+  SDXE_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SDXE_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return 0;
 }
 
 int skinny_linear_launch(const float* in, int ldi, const void* W, const float* b, const float* add, float* out, int ldo,
                          int M, int N, int K, bool silu_out, bool bf16, cudaStream_t s) {
   if (K % 8 || ldi % 4) { set_last_error(__FILE__, __LINE__, "skinny_linear: K % 8"); return -1; }
-  constexpr int MT = 16, NPW = 2;
-  const int warps = (N + NPW - 1) / NPW;
-  const int blocks = (warps + 3) / 4;
+  if (kernels_init() != 0) return -1;
+  const int Kp = (K + 31) & ~31;
+  const size_t smem = 16 * (size_t)(((Kp * 2 + 127) & ~127) + 64);
+  if (smem > 200 * 1024) { set_last_error(__FILE__, __LINE__, "skinny_linear: K too large for the activation stage"); return -1; }
+  const int blocks = (N + 8 * SKL_WARPS - 1) / (8 * SKL_WARPS);
   if (bf16)
-    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<true, MT, NPW>, dim3(blocks), dim3(128), 0, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
+    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<true>, dim3(blocks), dim3(SKL_WARPS * 32), smem, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
   else
-    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<false, MT, NPW>, dim3(blocks), dim3(128), 0, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
+    SDXE_CUDA_CHECK(launch_k(skinny_linear_kernel<false>, dim3(blocks), dim3(SKL_WARPS * 32), smem, s, in, ldi, (const uint4*)W, b, add, out, ldo, M, N, K, silu_out ? 1 : 0));
   SDXE_LAUNCH_CHECK();
   return 0;
 }
