@@ -95,6 +95,17 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int 
   return encode(out, base, 4, dims, strides, box);
 }
 
+// Stride-2 view of an NHWC activation (H, W even): [N, H/2, 2, W/2, 2C] — a pixel pair is one 2C-wide "pixel", a row pair
+// one extra dimension of size 2. Tap (dy, dx) of a 3x3 stride-2 conv reads input pixel (2 oh + ty, 2 ow + tx) with
+// t = d - pad_lo: row pair oh + (ty >> 1), row parity ty & 1, pixel pair ow + (tx >> 1), channel offset (tx & 1) * C — a
+// plain box per tap, out-of-range pairs zero-filled (the conv's padding). box = 64 channels x bw pairs x 1 x bh x bn.
+int make_tmap_nhwc_s2(CUtensorMap* out, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+  return encode(out, base, 5, dims, strides, box);
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

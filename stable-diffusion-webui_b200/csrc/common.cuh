@@ -125,6 +125,12 @@ SDXE_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, i
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+SDXE_DEVINL void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 
 // TMA store smem -> global (bulk async-group completion). The issuing thread commits and later waits on its own groups.
 SDXE_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -430,6 +436,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int
                  int box_rows);
 // 16-bit NHWC activations [N, H, W, C]: box = 64 ch x bw x bh x bn, 128B swizzle, OOB -> zero (= conv padding).
 int make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
+int make_tmap_nhwc_s2(CUtensorMap* out, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
 
 int num_sms();
 bool pdl_enabled();  // SDXE_PDL=1 turns programmatic dependent launch on (default off: measured 1-2 % slower)

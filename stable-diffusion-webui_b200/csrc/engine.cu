@@ -362,6 +362,36 @@ struct Builder {
     // generic geometry: explicit im2col (still CUDA; used for odd resolutions / narrow channel counts)
     return conv3_im2col(x, W, out, ldo, o, 1, 1, x.h, x.w);
   }
+  // 3x3 stride-2 conv (ldm Downsample): implicit GEMM over the pixel-pair view when the geometry allows it
+  int conv3_s2(const Act& x, const LinW& W, void* out, int ldo, const GemmOpt& o, int pad_lo, int Ho, int Wo) {
+    int bw, bh, bn;
+    static int implicit = -1;
+    if (implicit < 0) { const char* ev = getenv("SDXE_CONV_S2_IMPLICIT"); implicit = ev ? atoi(ev) : 1; }
+    if (implicit && x.c % 64 == 0 && x.h % 2 == 0 && x.w % 2 == 0 && Ho == x.h / 2 && Wo == x.w / 2 && W.ld == 9 * x.c &&
+        conv_tile_shape(Ho, Wo, &bw, &bh, &bn)) {
+      GemmArgs a;
+      memset(&a, 0, sizeof(a));
+      a.M = x.n * Ho * Wo; a.N = W.N; a.K = 9 * x.c; a.K1 = a.K;
+      a.conv = 2; a.pad_lo = pad_lo; a.cblocks = x.c / 64; a.H = Ho; a.W = Wo; a.bh = bh; a.bn = bn;
+      a.epi = EPI_PLAIN;
+      a.BN = gemm_pick_bn(a.M, a.N, a.K, a.epi);
+      ECHK(make_tmap_nhwc_s2(&a.tmA, x.p, x.n, x.h, x.w, x.c, bw, bh, bn));
+      a.tmA2 = a.tmA;
+      a.bias = W.b;
+      a.rowvec = o.rowvec; a.ldrv = o.ldrv; a.rows_per_sample = std::max(1, o.rows_per_sample);
+      a.residual = o.residual; a.ldr = o.ldr;
+      a.out = out; a.ldo = ldo;
+      ECHK(gemm_finish_args(a, W.w, std::max(W.N, W.Nrows), W.ld));
+      const bool b = bf16;
+      const double Md = (double)a.M;
+      const double by = 2.0 * (4.0 * Md * x.c + (double)W.N * a.K + Md * W.N);
+      char d[160];
+      snprintf(d, sizeof(d), "conv3s2 M=%d N=%d Cin=%d HoxWo=%dx%d BN=%d st=%d", a.M, W.N, x.c, Ho, Wo, a.BN, a.num_stages);
+      ops->push_back(OpRec([a, b](cudaStream_t s) { count_launch(); return gemm_launch(a, b, s); }, K_CONV, 2.0 * Md * W.N * a.K, by, d));
+      return 0;
+    }
+    return conv3_im2col(x, W, out, ldo, o, 2, pad_lo, Ho, Wo);
+  }
   int conv3_im2col(const Act& x, const LinW& W, void* out, int ldo, const GemmOpt& o, int stride, int pad_lo, int Ho, int Wo) {
     const int kpad = W.ld;
     const int64_t M = (int64_t)x.n * Ho * Wo;
@@ -1148,7 +1178,7 @@ int build_unet_plan(sdxe_engine* e, Plan* p, int n, int h, int w, int ctx_len) {
       const int Ho = (cur.h + 2 - 3) / 2 + 1, Wo = (cur.w + 2 - 3) / 2 + 1;
       Act d = B.new_act(n, Ho, Wo, b.ch_out);
       Builder::GemmOpt o;
-      ECHK(B.conv3_im2col(cur, b.down, d.p, b.ch_out, o, 2, 1, Ho, Wo));
+      ECHK(B.conv3_s2(cur, b.down, d.p, b.ch_out, o, 1, Ho, Wo));
       cur = d;
     }
     hs.push_back(cur);
@@ -1289,7 +1319,7 @@ int build_vae_encode_plan(sdxe_engine* e, Plan* p, int n, int H, int W) {
       // ldm Downsample (with_conv): pad (0,1,0,1) then conv3x3 stride 2, padding 0 -> taps start at the pixel itself
       const int Ho = cur.h / 2, Wo = cur.w / 2;
       Act d = B.new_act(n, Ho, Wo, cur.c);
-      ECHK(B.conv3_im2col(cur, e->e_down_conv[level], d.p, cur.c, Builder::GemmOpt(), 2, 0, Ho, Wo));
+      ECHK(B.conv3_s2(cur, e->e_down_conv[level], d.p, cur.c, Builder::GemmOpt(), 0, Ho, Wo));
       B.free_act(cur);
       cur = d;
     }

@@ -165,7 +165,11 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
             tma2_load_2d(sB, &a.tmB, fb, kb * BLOCK_K, n_blk * BN + (int)crank * (BN >> 1));  // my half of B
           } else {
             mbar_expect_tx(fb, stage_bytes);
-            if (a.conv) {
+            if (a.conv == 2) {  // stride 2: (pixel pair, parity) addressing of the 5-D view, see make_tmap_nhwc_s2
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const int ty = dy - a.pad_lo, tx = dx - a.pad_lo;
+              tma_load_5d(sA, &a.tmA, fb, (tx & 1) * (a.cblocks * BLOCK_K) + cb * BLOCK_K, w0 + (tx >> 1), ty & 1, h0 + (ty >> 1), img0);
+            } else if (a.conv) {
               const int dy = tap / 3, dx = tap - dy * 3;
               tma_load_4d(sA, &a.tmA, fb, cb * BLOCK_K, w0 + dx - 1, h0 + dy - 1, img0);
             } else {
@@ -571,7 +575,7 @@ int gemm_pick_stages(int BN, int epi_bufs) {
   return std::max(2, std::min(s, 8));
 }
 int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld) {
-  a.cluster = (a.c1 || a.stat_out) ? 1 : gemm_pick_cluster(a.M, a.BN);  // fold / statistics variants are un-paired only
+  a.cluster = (a.c1 || a.stat_out || a.conv == 2) ? 1 : gemm_pick_cluster(a.M, a.BN);  // fold / statistics / stride-2 variants are un-paired only
   const int bn_cta = a.cluster == 2 ? a.BN / 2 : a.BN;
   // one staging buffer more than the minimum unless that costs an operand stage below four
   const int min_bufs = a.residual ? 2 : 1;
