@@ -25,6 +25,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef SDXE_GEMM_TRACE
+#define SDXE_GEMM_TRACE 0
+#endif
+
 namespace sdxe {
 
 static constexpr int BLOCK_M = 128;
@@ -78,6 +82,19 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#if SDXE_GEMM_TRACE
+  // timeline of CTA 0: [role 0 producer | 1 MMA | 2 first epilogue warp | 3 last epilogue warp][tile < 40][event < 4]
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0;
+  auto TR = [&](int role, int it, int ev) {
+    if (tracing && lane == 0 && it < 40) {
+      unsigned long long c;
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+      a.trace[(role * 40 + it) * 4 + ev] = c;
+    }
+  };
+#else
+#define TR(role, it, ev) ((void)0)
+#endif
 
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (a.N + BN - 1) / BN;
@@ -144,8 +161,10 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         w0 = rem - h0 * a.W;
       }
       int tap = 0, cb = 0;  // conv: k-block -> (tap, channel block) without divisions
+      TR(0, (tile - work_first) / work_step, 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (kb == 0) TR(0, (tile - work_first) / work_step, 1);
         if (elect_one()) {
           const uint32_t sA = smem_base + stage * stage_bytes;
           const uint32_t sB = sA + A_STAGE_BYTES;
@@ -184,6 +203,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         if (++cb == a.cblocks) { cb = 0; ++tap; }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      TR(0, (tile - work_first) / work_step, 2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -198,12 +218,15 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = work_first; tile < num_tiles; tile += work_step) {
+        TR(1, (tile - work_first) / work_step, 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        TR(1, (tile - work_first) / work_step, 1);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kb == 0) TR(1, (tile - work_first) / work_step, 2);
           if (elect_one()) {
             const uint64_t adesc = adesc0 + (uint64_t)(stage * stage_inc);
             const uint64_t bdesc = bdesc0 + (uint64_t)(stage * stage_inc);
@@ -230,6 +253,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
           else tc_commit(tfull_bar(acc));
         }
         __syncwarp();
+        TR(1, (tile - work_first) / work_step, 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -279,8 +303,10 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         ln_rs = rsqrtf(fmaxf(pq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * GEGLU_EPI_WARPS) : "memory");  // bias of this tile visible to all epilogue warps
+      if (ew == 0 || ew == GEGLU_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (ew == 0 || ew == GEGLU_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 1);
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       for (int c0 = esub * 16; c0 < half; c0 += 64, ++chunk_ctr) {
         const uint32_t buf = my_buf + (chunk_ctr % (uint32_t)NBUF) * GEGLU_CHUNK_BYTES;
@@ -342,6 +368,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
       }
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 || ew == GEGLU_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 2);
       if (lane == 0) {
         if (clustered && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
         else mbar_arrive(tempty_bar(acc));
@@ -414,8 +441,10 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         __syncwarp();
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all epilogue warps
+      if (ew == 0 || ew == NUM_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (ew == 0 || ew == NUM_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 1);
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const float* rv = nullptr;
       if (ROWVEC && row_ok) rv = a.rowvec + (size_t)(m / a.rows_per_sample) * a.ldrv + n_out0;
@@ -526,6 +555,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
       if (STAT && row_ok) a.stat_out[(size_t)(n_blk * 2 + ehalf) * M + m] = make_float2(st_s, st_q);
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 || ew == NUM_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 2);
       if (lane == 0) {
         if (clustered && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);  // the leader's MMA lane owns the accumulators
         else mbar_arrive(tempty_bar(acc));
@@ -658,7 +688,38 @@ int gemm_init() {
   return 0;
 }
 
+#if SDXE_GEMM_TRACE
+// SDXE_GEMM_TRACE_DUMP=<n>: the n-th gemm_launch of the process (1-based) runs with the timeline buffer and writes
+// gpurun_out/gemm_trace.txt (tools/analyze_gemm_trace.py). Debug builds only (make GEMM_TRACE=1).
+static int gemm_launch_inner(const GemmArgs& a, bool bf16, cudaStream_t stream);
+int gemm_launch(const GemmArgs& a0, bool bf16, cudaStream_t stream) {
+  static int want = -1, count = 0;
+  static unsigned long long* buf = nullptr;
+  if (want < 0) { const char* e = getenv("SDXE_GEMM_TRACE_DUMP"); want = e ? atoi(e) : 0; }
+  if (!want || ++count != want) return gemm_launch_inner(a0, bf16, stream);
+  GemmArgs a = a0;
+  const size_t bytes = 4 * 40 * 4 * 8;
+  if (!buf) cudaMalloc(&buf, bytes);
+  cudaMemsetAsync(buf, 0, bytes, stream);
+  a.trace = buf;
+  const int rc = gemm_launch_inner(a, bf16, stream);
+  cudaStreamSynchronize(stream);
+  static unsigned long long h[4 * 40 * 4];
+  cudaMemcpy(h, buf, bytes, cudaMemcpyDeviceToHost);
+  FILE* f = fopen("gpurun_out/gemm_trace.txt", "w");
+  if (f) {
+    fprintf(f, "# M=%d N=%d K=%d BN=%d stages=%d epi=%d res=%d conv=%d\n", a.M, a.N, a.K, a.BN, a.num_stages, a.epi, a.residual ? 1 : 0, a.conv);
+    for (int r = 0; r < 4; ++r)
+      for (int t = 0; t < 40; ++t)
+        fprintf(f, "%d %d %llu %llu %llu %llu\n", r, t, h[(r * 40 + t) * 4], h[(r * 40 + t) * 4 + 1], h[(r * 40 + t) * 4 + 2], h[(r * 40 + t) * 4 + 3]);
+    fclose(f);
+  }
+  return rc;
+}
+static int gemm_launch_inner(const GemmArgs& a, bool bf16, cudaStream_t stream) {
+#else
 int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
+#endif
   if (a.BN % 16 != 0 || a.BN < 16 || a.BN > 256) { set_last_error(__FILE__, __LINE__, "gemm: bad BN"); return -1; }
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
