@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * S + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * S + 2 + i); };
-  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * S + 4 + 3 * w + b); };
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * S + 4 + 4 * w + b); };  // <= 4 residual buffers per warp
   const uint32_t misc_off = S * stage_bytes + 8 * (2 * S + NUM_BARS_FIXED);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + misc_off);
   float* sbias = reinterpret_cast<float*>(smem + misc_off + 16);  // [2][256]
@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 #if SDXE_GEMM_TRACE
-  // timeline of CTA 0: [role 0 producer | 1 MMA | 2 first epilogue warp | 3 last epilogue warp][tile < 40][event < 4]
+  // timeline of CTA 0: [role 0 producer | 1 MMA | 2 first epilogue warp | 3 last epilogue warp |
+  // 4, 5 first epilogue warp inside its first chunk: ld issued, ld done, arithmetic done, buffer free | stored, fenced, TMA issued][tile < 40][event < 4]
   const bool tracing = a.trace != nullptr && blockIdx.x == 0;
   auto TR = [&](int role, int it, int ev) {
     if (tracing && lane == 0 && it < 40) {
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
       mbar_init(tempty_bar(i), (EPI == EPI_GEGLU ? GEGLU_EPI_WARPS : NUM_EPI_WARPS) * (clustered ? 2 : 1));
     }
     if (RES)
-      for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); mbar_init(res_bar(w, 2), 1); }
+      for (int w = 0; w < NUM_EPI_WARPS; ++w)
+        for (int b = 0; b < 4; ++b) mbar_init(res_bar(w, b), 1);
     fence_mbar_init();
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
@@ -398,6 +400,29 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
     const float* const biasp = a.bias;
     const int M = a.M, N = a.N;
     const uint32_t my_buf = stage_buf_base + (uint32_t)(ew * NBUF) * CHUNK_BYTES;
+    // RES: this warp's residual chunks form one stream across its tiles; a prefetch cursor runs a.res_dist chunks ahead
+    // of the chunk being processed (also across tile boundaries), each chunk TMA-loaded into the staging buffer it will
+    // be updated in and stored from. (Distance 1 left ~0.6 k cycles of residual latency in every chunk's chain and the
+    // whole latency at each tile start: profiles/r2_gemm_epilogue_trace.txt.)
+    int p_tile = work_first, p_c0 = ehalf * 32;
+    uint32_t p_ctr = 0;
+    auto res_prefetch = [&]() {  // elected lane only
+      if (p_tile >= num_tiles || p_c0 >= out_cols) return;
+      const int pn = p_tile % num_n;
+      const int pm = clustered ? 2 * (p_tile / num_n) + (int)crank : p_tile / num_n;
+      const uint32_t pb = p_ctr % (uint32_t)NBUF;
+      const int nc = min(32, out_cols - p_c0);
+      mbar_expect_tx(res_bar(ew, pb), (uint32_t)nc * 64u);
+      tma_load_2d(my_buf + pb * CHUNK_BYTES, nc == 32 ? &a.tmR : &a.tmR16, res_bar(ew, pb), pn * out_cols + p_c0, pm * BLOCK_M + quarter * 32);
+      ++p_ctr;
+      p_c0 += 64;
+      if (p_c0 >= out_cols) { p_c0 = ehalf * 32; p_tile += work_step; }
+    };
+    if (RES) {
+      if (elect_one())
+        for (int i = 0; i < a.res_dist; ++i) res_prefetch();  // buffers are fresh: nothing to wait for
+      __syncwarp();
+    }
     for (int tile = work_first; tile < num_tiles; tile += work_step, ++tile_ctr) {
       const int n_blk = tile % num_n;
       const int m_blk = clustered ? 2 * (tile / num_n) + (int)crank : tile / num_n;
@@ -426,20 +451,6 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         ln_rs = rsqrtf(fmaxf(pq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
       }
       float st_s = 0.f, st_q = 0.f;  // STAT: this thread's share of its row's (sum, sum of squares)
-      auto res_load = [&](int c0, uint32_t ctr) {  // elected lane: residual chunk -> staging buffer ctr % NBUF
-        const uint32_t b = ctr % (uint32_t)NBUF;
-        const int nc = min(32, out_cols - c0);
-        mbar_expect_tx(res_bar(ew, b), (uint32_t)nc * 64u);
-        tma_load_2d(my_buf + b * CHUNK_BYTES, nc == 32 ? &a.tmR : &a.tmR16, res_bar(ew, b), n_out0 + c0, row0);
-      };
-      if (RES && ehalf * 32 < out_cols) {  // (a tile narrower than 33 columns leaves the second warp of a quarter idle)
-        // first chunk's residual travels while the accumulator is still being produced
-        if (elect_one()) {
-          if (deep) bulk_wait_read_1(); else bulk_wait_read_all();
-          res_load(ehalf * 32, chunk_ctr);
-        }
-        __syncwarp();
-      }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all epilogue warps
       if (ew == 0 || ew == NUM_EPI_WARPS - 1) TR(ew == 0 ? 2 : 3, (int)tile_ctr, 0);
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -455,18 +466,22 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
         const uint32_t b = chunk_ctr % (uint32_t)NBUF;
         const uint32_t buf = my_buf + b * CHUNK_BYTES;
         uint32_t r[32];
+        const bool trc = ew == 0 && c0 == 0;  // (trace builds) stamps inside the first warp's first chunk
+        if (trc) TR(4, (int)tile_ctr, 0);
         if (nc == 32) tmem_ld32(t_row + c0, r);
         else tmem_ld16(t_row + c0, r);
         if (RES) {
-          // the other buffer is free once the previous chunk's store has read it: fetch the next residual chunk into it
+          // keep the residual stream res_dist chunks ahead: the buffer of chunk c + res_dist was last read by the store of
+          // chunk c + res_dist - NBUF, which may have one younger store still in flight (deep) or none
           if (elect_one()) {
-            if (deep) bulk_wait_read_1(); else bulk_wait_read_all();  // the next chunk's buffer was read by store(c-2) / store(c-1)
-            if (c0 + 64 < out_cols) res_load(c0 + 64, chunk_ctr + 1);
+            if (deep) bulk_wait_read_1(); else bulk_wait_read_all();
+            res_prefetch();
           }
           __syncwarp();
           mbar_wait(res_bar(ew, b), (chunk_ctr / (uint32_t)NBUF) & 1u);
         }
         tc_wait_ld();
+        if (trc) TR(4, (int)tile_ctr, 1);
         // this thread's row piece inside the chunk: 16-byte unit g at (lane * rowbytes + 16 g) ^ swizzle
         const uint32_t lin0 = (uint32_t)lane * (uint32_t)(nc * 2);
         const uint32_t swz_mask = nc == 32 ? 3u : 1u;  // 64B / 32B swizzle: unit index ^= address bits [7, 8] / [7]
@@ -529,11 +544,13 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
             }
           }
         }
+        if (trc) TR(4, (int)tile_ctr, 2);
         if (!RES) {
           // this buffer was last read by the store of chunk c - NBUF: it must be done before the buffer is overwritten
           if (elect_one()) { if (deep) bulk_wait_read_1(); else bulk_wait_read_all(); }
           __syncwarp();
         }
+        if (trc) TR(4, (int)tile_ctr, 3);
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
           if (g < nc) {
@@ -544,13 +561,16 @@ __global__ void __launch_bounds__(EPI == EPI_GEGLU ? GEGLU_THREADS : GEMM_THREAD
                          : "memory");
           }
         }
+        if (trc) TR(5, (int)tile_ctr, 0);
         fence_proxy_async_smem();
         __syncwarp();
+        if (trc) TR(5, (int)tile_ctr, 1);
         if (elect_one()) {
           tma_store_2d(nc == 32 ? &a.tmO : &a.tmO16, buf, n_out0 + c0, row0);
           bulk_commit_group();
         }
         __syncwarp();
+        if (trc) TR(5, (int)tile_ctr, 2);
       }
       if (STAT && row_ok) a.stat_out[(size_t)(n_blk * 2 + ehalf) * M + m] = make_float2(st_s, st_q);
       tc_fence_before();
@@ -608,12 +628,22 @@ int gemm_finish_args(GemmArgs& a, const void* W, int64_t w_rows, int64_t w_ld) {
   a.cluster = (a.c1 || a.stat_out || a.conv == 2) ? 1 : gemm_pick_cluster(a.M, a.BN);  // fold / statistics / stride-2 variants are un-paired only
   const int bn_cta = a.cluster == 2 ? a.BN / 2 : a.BN;
   // one staging buffer more than the minimum unless that costs an operand stage below four
-  const int min_bufs = a.residual ? 2 : 1;
+  int min_bufs = a.residual ? 2 : 1;
+  a.res_dist = 1;
+  if (a.residual) {
+    // residual prefetch distance 2 needs four staging buffers per epilogue warp (64 KB): taken when the operand ring keeps
+    // at least min(k-blocks, 3) stages and the GEMM is short (K <= 640: epilogue-paced) or loses no stage to it
+    static int dist2 = -1;
+    if (dist2 < 0) { const char* e = getenv("SDXE_RES_DIST2"); dist2 = e ? atoi(e) : 1; }
+    const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+    const int s4 = gemm_pick_stages(bn_cta, 4);
+    if (dist2 && !a.conv && s4 >= std::min(num_kb, 3) && (num_kb <= 10 || s4 == gemm_pick_stages(bn_cta, 2))) { min_bufs = 4; a.res_dist = 2; }
+  }
   const int s_min = gemm_pick_stages(bn_cta, min_bufs), s_deep = gemm_pick_stages(bn_cta, min_bufs + 1);
   static int deep_ok = -1;
   // default off: measured no gain (same-box A/B, SD1.5 UNet 18.74 / 18.76 ms with vs 18.65 / 18.98 ms without)
   if (deep_ok < 0) { const char* e = getenv("SDXE_EPI_DEEP"); deep_ok = e ? atoi(e) : 0; }
-  a.epi_bufs = (deep_ok && (s_deep == s_min || s_deep >= 4)) ? min_bufs + 1 : min_bufs;
+  a.epi_bufs = (min_bufs < 4 && deep_ok && (s_deep == s_min || s_deep >= 4)) ? min_bufs + 1 : min_bufs;
   a.num_stages = a.epi_bufs > min_bufs ? s_deep : s_min;
   if (make_tmap_2d(&a.tmB, W, w_rows, a.K, w_ld, bn_cta)) return -1;
   const int64_t out_cols = a.epi == EPI_GEGLU ? a.N / 2 : (a.N + 7) / 8 * 8;
@@ -698,18 +728,18 @@ int gemm_launch(const GemmArgs& a0, bool bf16, cudaStream_t stream) {
   if (want < 0) { const char* e = getenv("SDXE_GEMM_TRACE_DUMP"); want = e ? atoi(e) : 0; }
   if (!want || ++count != want) return gemm_launch_inner(a0, bf16, stream);
   GemmArgs a = a0;
-  const size_t bytes = 4 * 40 * 4 * 8;
+  const size_t bytes = 6 * 40 * 4 * 8;
   if (!buf) cudaMalloc(&buf, bytes);
   cudaMemsetAsync(buf, 0, bytes, stream);
   a.trace = buf;
   const int rc = gemm_launch_inner(a, bf16, stream);
   cudaStreamSynchronize(stream);
-  static unsigned long long h[4 * 40 * 4];
+  static unsigned long long h[6 * 40 * 4];
   cudaMemcpy(h, buf, bytes, cudaMemcpyDeviceToHost);
   FILE* f = fopen("gpurun_out/gemm_trace.txt", "w");
   if (f) {
     fprintf(f, "# M=%d N=%d K=%d BN=%d stages=%d epi=%d res=%d conv=%d\n", a.M, a.N, a.K, a.BN, a.num_stages, a.epi, a.residual ? 1 : 0, a.conv);
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 6; ++r)
       for (int t = 0; t < 40; ++t)
         fprintf(f, "%d %d %llu %llu %llu %llu\n", r, t, h[(r * 40 + t) * 4], h[(r * 40 + t) * 4 + 1], h[(r * 40 + t) * 4 + 2], h[(r * 40 + t) * 4 + 3]);
     fclose(f);
@@ -724,7 +754,7 @@ int gemm_launch(const GemmArgs& a, bool bf16, cudaStream_t stream) {
   if (a.K1 != a.K && (a.K1 % BLOCK_K) != 0) { set_last_error(__FILE__, __LINE__, "gemm: K1 % 64"); return -1; }
   if (a.epi == EPI_GEGLU && (a.BN % 32 != 0 || a.N % a.BN != 0)) { set_last_error(__FILE__, __LINE__, "gemm: geglu tile"); return -1; }
   const int stage_bytes = A_STAGE_BYTES + (a.cluster == 2 ? a.BN / 2 : a.BN) * 128;
-  if (a.epi_bufs < (a.residual ? 2 : 1) || a.epi_bufs > 3) { set_last_error(__FILE__, __LINE__, "gemm: epi_bufs (call gemm_finish_args)"); return -1; }
+  if (a.epi_bufs < (a.residual ? 2 : 1) || a.epi_bufs > 4 || (a.residual && (a.res_dist < 1 || a.res_dist > a.epi_bufs - 1))) { set_last_error(__FILE__, __LINE__, "gemm: epi_bufs (call gemm_finish_args)"); return -1; }
   const size_t smem = (size_t)a.num_stages * stage_bytes + gemm_smem_fixed(a.num_stages, a.epi_bufs);
   if (smem > 227 * 1024) { set_last_error(__FILE__, __LINE__, "gemm: shared memory budget"); return -1; }
   const int num_m = (a.M + BLOCK_M - 1) / BLOCK_M, num_n = (a.N + a.BN - 1) / a.BN;

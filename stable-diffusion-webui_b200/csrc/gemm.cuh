@@ -22,7 +22,8 @@ struct alignas(64) GemmArgs {
   int K1;            // K elements sourced from tmA (== K when there is no second segment)
   int BN;            // tile width (multiple of 16, <= 256)
   int num_stages;
-  int epi_bufs;      // staging chunks per epilogue warp (set by gemm_finish_args): plain 1-2, residual 2-3
+  int epi_bufs;      // staging chunks per epilogue warp (set by gemm_finish_args): plain 1-2, residual 2-4
+  int res_dist;      // residual prefetch distance in chunks (set by gemm_finish_args): 1, or 2 with four buffers
   unsigned long long* trace;  // SDXE_GEMM_TRACE builds: clock64 timeline of CTA 0 (see gemm.cu), else unused
   int conv;          // 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 NHWC implicit GEMM, 2 = 3x3 stride-2 (tmA = make_tmap_nhwc_s2)
   int pad_lo;        // conv == 2: zero rows / columns before the image (1: ldm UNet Downsample, 0: VAE encoder pad (0,1,0,1))
