@@ -7,8 +7,10 @@
                                        (+ DiffusionWrapper, modules/models/diffusion/ddpm_edit.py:1417-1437;
                                         SDXL: modules/sd_models_xl.py:37-43)
 
-Text encoders, PNG/infotext, scripts and the UI are outside the accelerated path: conditionings arrive as tensors
-(what `p.setup_conds()` leaves in p.c / p.uc), images leave as a uint8 tensor.
+PNG/infotext, scripts and the UI are outside the accelerated path. Conditionings arrive either as tensors / containers
+(what `p.setup_conds()` leaves in p.c / p.uc) or as prompts: with `prompts` set and a conditioner attached to the model,
+`setup_conds()` (modules/processing.py:460-506, 1498-1542) builds p.c / p.uc / p.hr_c / p.hr_uc itself — prompt editing,
+alternation and AND-composition through prompt_parser, text encoders on the engine. Images leave as a uint8 tensor.
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ from typing import List, Optional
 import torch
 
 from . import lib as L
+from . import prompt_parser
 from . import samplers as S
 from .engine import VAEDecoderEngine
 from .rng import ImageRNG
@@ -41,6 +44,24 @@ class SdModel:
         self.scale_factor = scale_factor if scale_factor is not None else (0.13025 if is_sdxl else 0.18215)
         self.alphas_cumprod = S.make_alphas_cumprod().to(self.device)
         self.parameterization = "eps"
+        # the conditioner (N4): SD1.x — a TextConditionalModel (sd_hijack_clip.FrozenCLIPEmbedderWithCustomWords); SDXL — the pair
+        # (FrozenCLIPEmbedderForSDXLWithCustomWords, FrozenOpenCLIPEmbedder2WithCustomWords). None: conds must arrive as tensors.
+        self.cond_stage_model = None
+        self.sdxl_crop_top, self.sdxl_crop_left = 0, 0   # opts.sdxl_crop_top / sdxl_crop_left
+
+    def get_learned_conditioning(self, texts):
+        """LatentDiffusion.get_learned_conditioning (`cond_stage_model(texts)`); SDXL: modules/sd_models_xl.py:12-34 — width /
+        height / is_negative_prompt travel on the SdConditioning list."""
+        if self.cond_stage_model is None:
+            raise L.SdxeError("no text encoder attached to the model (set SdModel.cond_stage_model or pass conds as tensors)")
+        if not self.is_sdxl:
+            return self.cond_stage_model(texts)
+        from .sd_hijack_clip import sdxl_get_learned_conditioning
+
+        clip_l, clip_g = self.cond_stage_model
+        return sdxl_get_learned_conditioning(clip_l, clip_g, list(texts), width=getattr(texts, "width", None) or 1024,
+                                             height=getattr(texts, "height", None) or 1024, crop_top=self.sdxl_crop_top,
+                                             crop_left=self.sdxl_crop_left, is_negative_prompt=getattr(texts, "is_negative_prompt", False))
 
     def apply_model(self, x_noisy, t, cond=None, **kwargs):
         """cast to dtype_unet, call the UNet through the SdUnet seam (sd_hijack_unet.py:40-54)."""
@@ -123,9 +144,89 @@ class StableDiffusionProcessingTxt2Img:
     rng: ImageRNG = None
     sampler: S.KDiffusionSampler = None
     is_hr_pass: bool = False
+    # prompt-driven conditioning (modules/processing.py:460-506): one prompt per image; None -> c / uc are given
+    prompts: Optional[List[str]] = None
+    negative_prompts: Optional[List[str]] = None
+    hr_prompts: Optional[List[str]] = None            # default: the first-pass prompts
+    hr_negative_prompts: Optional[List[str]] = None
+    use_old_scheduling: bool = False                  # opts.use_old_scheduling
+    hr_c: object = None
+    hr_uc: object = None
+    step_multiplier: int = 1
+    firstpass_steps: int = 0
+    # class-level in the reference (shared between jobs so that an unchanged prompt is not re-encoded): [params, result]
+    cached_uc = [None, None]
+    cached_c = [None, None]
+    cached_hr_uc = [None, None]
+    cached_hr_c = [None, None]
 
     def __post_init__(self):
         self.batch_size = len(self.seeds)
+
+    # ---- prompts -> conditioning ------------------------------------------------------------------------------------
+    def cached_params(self, required_prompts, steps, hires_steps, use_old_scheduling):
+        """modules/processing.py:436-458 (the options that change what the conditioner returns)."""
+        m = self.sd_model
+        return (tuple(required_prompts), steps, hires_steps, use_old_scheduling, id(m), id(m.cond_stage_model) if m is not None else None,
+                getattr(required_prompts, "width", None), getattr(required_prompts, "height", None),
+                getattr(required_prompts, "is_negative_prompt", False), getattr(m, "sdxl_crop_top", 0), getattr(m, "sdxl_crop_left", 0))
+
+    def get_conds_with_caching(self, function, required_prompts, steps, caches, hires_steps=None):
+        """:460-491 — `caches` are [params, result] pairs; a hit in any of them is returned, a miss fills the first."""
+        params = self.cached_params(required_prompts, steps, hires_steps, self.use_old_scheduling)
+        for cache in caches:
+            if cache[0] is not None and params == cache[0]:
+                return cache[1]
+        cache = caches[0]
+        cache[1] = function(self.sd_model, required_prompts, steps, hires_steps, self.use_old_scheduling)
+        cache[0] = params
+        return cache[1]
+
+    def _total_steps(self, sampler_name, steps):
+        config = S.find_sampler_config(sampler_name)   # second-order samplers call the denoiser twice per step (:497-498)
+        return steps * 2 if config is not None and config[2].get("second_order", False) else steps
+
+    def setup_conds(self):
+        """:493-503 and :1513-1527."""
+        if self.prompts is None:
+            return
+        if self.is_hr_pass:
+            self.hr_c = None
+            self.calculate_hr_conds()
+            return
+        negatives = self.negative_prompts if self.negative_prompts is not None else [""] * len(self.prompts)
+        prompts = prompt_parser.SdConditioning(self.prompts, width=self.width, height=self.height)
+        negative_prompts = prompt_parser.SdConditioning(negatives, width=self.width, height=self.height, is_negative_prompt=True)
+        total_steps = self._total_steps(self.sampler_name, self.steps)
+        self.step_multiplier = total_steps // self.steps
+        self.firstpass_steps = total_steps
+        cls = type(self)
+        self.uc = self.get_conds_with_caching(prompt_parser.get_learned_conditioning, negative_prompts, total_steps, [cls.cached_uc])
+        self.c = self.get_conds_with_caching(prompt_parser.get_multicond_learned_conditioning, prompts, total_steps, [cls.cached_c])
+        self.hr_uc = None
+        self.hr_c = None
+
+    def calculate_hr_conds(self):
+        """:1498-1511 — the second pass counts whole-number `when` on from the first pass's steps and fractions from 1.0."""
+        if self.hr_c is not None or self.prompts is None:
+            return
+        tw, th = int(self.width * self.hr_scale), int(self.height * self.hr_scale)
+        hr_p = self.hr_prompts if self.hr_prompts is not None else self.prompts
+        hr_n = self.hr_negative_prompts if self.hr_negative_prompts is not None else (self.negative_prompts if self.negative_prompts is not None else [""] * len(hr_p))
+        hr_prompts = prompt_parser.SdConditioning(hr_p, width=tw, height=th)
+        hr_negative_prompts = prompt_parser.SdConditioning(hr_n, width=tw, height=th, is_negative_prompt=True)
+        total_steps = self._total_steps(self.sampler_name, self.hr_second_pass_steps or self.steps)
+        cls = type(self)
+        self.hr_uc = self.get_conds_with_caching(prompt_parser.get_learned_conditioning, hr_negative_prompts, self.firstpass_steps,
+                                                 [cls.cached_hr_uc, cls.cached_uc], total_steps)
+        self.hr_c = self.get_conds_with_caching(prompt_parser.get_multicond_learned_conditioning, hr_prompts, self.firstpass_steps,
+                                                [cls.cached_hr_c, cls.cached_c], total_steps)
+
+    def get_conds(self):
+        """:505-506, :1538-1542."""
+        if self.is_hr_pass and self.hr_c is not None:
+            return self.hr_c, self.hr_uc
+        return self.c, self.uc
 
     def make_rng(self, shape, seeds) -> ImageRNG:
         return ImageRNG(shape, seeds, subseeds=self.subseeds, subseed_strength=self.subseed_strength,
@@ -150,7 +251,9 @@ class StableDiffusionProcessingTxt2Img:
         self.rng = self.make_rng(shape, seeds)                                     # processing.py:1429
         noise = self.rng.next()
         self.sampler = S.create_sampler(self.sampler_name, self.sd_model)
-        return self.sampler.sample_img2img(self, samples, noise, self.c, self.uc, steps=self.hr_second_pass_steps or self.steps)
+        self.calculate_hr_conds()                                                  # processing.py:1447 (no-op without prompts)
+        c, uc = self.get_conds()
+        return self.sampler.sample_img2img(self, samples, noise, c, uc, steps=self.hr_second_pass_steps or self.steps)
 
 
 @dataclass
@@ -246,6 +349,8 @@ def process_images(p: StableDiffusionProcessingTxt2Img, to_host: bool = True) ->
     S.state.skipped = False
     dev = p.sd_model.device
     with torch.cuda.device(dev):
+        p.is_hr_pass = False
+        p.setup_conds()                                                                       # processing.py:966 (no-op without prompts)
         p.rng = p.make_rng((opt_C, p.height // opt_f, p.width // opt_f), p.seeds)           # processing.py:949
         samples = p.sample(p.c, p.uc, p.seeds)
         if p.do_not_decode:

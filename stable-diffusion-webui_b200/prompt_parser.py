@@ -194,3 +194,230 @@ def get_multicond_prompt_list(prompts):
             parts.append((index_of[text], weight))
         per_prompt.append(parts)
     return per_prompt, flat, index_of
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Prompt editing: "[from:to:when]", "[to:when]", "[from::when]", alternation "[a|b|...]" -> per-prompt step schedules
+# (modules/prompt_parser.py:14-147), then prompt -> conditioning schedules (:155-203, :246-262).
+#
+# The reference parses with a lark (Earley) grammar. Restated here as a hand-written packrat parser of the same language —
+# no parser generator on the product path:
+#   start     : (prompt | one of the characters [ ] ( ) : )*                 stray delimiters are legal at top level only
+#   prompt    : (emphasized | scheduled | alternate | plain)*
+#   emphasized: "(" prompt ")" | "(" prompt ":" prompt ")" | "[" prompt "]"   (kept verbatim in the output text)
+#   scheduled : "[" [prompt ":"] prompt ":" ws? NUMBER ws? "]"
+#   alternate : "[" prompt ("|" prompt?)+ "]"
+#   plain     : runs of characters other than \ [ ] ( ) : |  or backslash-escaped characters (whitespace included)
+# A bracket that cannot be completed as one of the constructs is a stray delimiter; a bare "|" (or a trailing backslash)
+# makes the prompt unparseable and it is then used unscheduled, as the reference does on a parse error. Pinned against the
+# reference's doctests (:30-62) and a fuzz corpus run through the reference itself (tests/golden/prompt_sched_ref.json).
+# ----------------------------------------------------------------------------------------------------------------------
+_PLAIN = re.compile(r"(?:[^\\\[\]():|]|\\.)+")
+_WS = re.compile(r"\s+")
+_SIGNED_NUMBER = re.compile(r"[+-]?(?:\d+\.\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+|\d+)")
+_STRAY = "[]():"
+
+
+class _ScheduleSyntax:
+    """Packrat recursive descent over one prompt. Nodes: str (verbatim text), ("seq", [nodes]),
+    ("sched", before | None, after, number_text), ("alt", [option | None, ...])."""
+
+    def __init__(self, text: str):
+        self.text = text
+        self.memo = {}
+
+    def prompt(self, pos: int):
+        """Longest run of elements starting at pos -> (("seq", nodes), end). Never fails (may be empty)."""
+        nodes = []
+        text = self.text
+        while pos < len(text):
+            ch = text[pos]
+            if ch == "(" or ch == "[":
+                got = self.construct(pos)
+                if got is None:
+                    break
+                node, pos = got
+                nodes.append(node)
+                continue
+            m = _PLAIN.match(text, pos)
+            if m is None:
+                break
+            nodes.append(m.group(0))
+            pos = m.end()
+        return ("seq", nodes), pos
+
+    def construct(self, pos: int):
+        if pos not in self.memo:
+            self.memo[pos] = self._paren(pos) if self.text[pos] == "(" else self._bracket(pos)
+        return self.memo[pos]
+
+    def _at(self, pos: int) -> str:
+        return self.text[pos] if pos < len(self.text) else ""
+
+    def _paren(self, pos: int):
+        inner, p = self.prompt(pos + 1)
+        if self._at(p) == ")":
+            return ("seq", ["(", inner, ")"]), p + 1
+        if self._at(p) == ":":
+            second, q = self.prompt(p + 1)
+            if self._at(q) == ")":
+                return ("seq", ["(", inner, ":", second, ")"]), q + 1
+        return None
+
+    def _when(self, pos: int):
+        """ws? NUMBER ws? "]" -> (number text, end) | None"""
+        m = _WS.match(self.text, pos)
+        if m:
+            pos = m.end()
+        m = _SIGNED_NUMBER.match(self.text, pos)
+        if m is None:
+            return None
+        number, pos = m.group(0), m.end()
+        m = _WS.match(self.text, pos)
+        if m:
+            pos = m.end()
+        return (number, pos + 1) if self._at(pos) == "]" else None
+
+    def _bracket(self, pos: int):
+        first, p = self.prompt(pos + 1)
+        ch = self._at(p)
+        if ch == "]":
+            return ("seq", ["[", first, "]"]), p + 1
+        if ch == "|":
+            options = [first if first[1] else None]
+            while self._at(p) == "|":
+                option, p = self.prompt(p + 1)
+                options.append(option if option[1] else None)
+            return (("alt", options), p + 1) if self._at(p) == "]" else None
+        if ch == ":":
+            when = self._when(p + 1)
+            if when is not None:                       # "[to:when]"
+                return ("sched", None, first, when[0]), when[1]
+            second, q = self.prompt(p + 1)
+            if self._at(q) == ":":
+                when = self._when(q + 1)
+                if when is not None:                   # "[from:to:when]"
+                    return ("sched", first if first[1] else None, second, when[0]), when[1]
+        return None
+
+    def parse(self):
+        """-> top-level node list, or None when the prompt is not in the language."""
+        nodes, pos, text = [], 0, self.text
+        while pos < len(text):
+            (_, part), pos = self.prompt(pos)
+            nodes.extend(part)
+            if pos >= len(text):
+                break
+            if text[pos] in _STRAY:
+                nodes.append(text[pos])
+                pos += 1
+            else:
+                return None
+        return nodes
+
+
+def get_learned_conditioning_prompt_schedules(prompts, base_steps, hires_steps=None, use_old_scheduling=False):
+    """modules/prompt_parser.py:26-147: every prompt -> [[end_at_step, text], ...]. Whole-number `when` is a step, a `when`
+    with a decimal point a fraction of the pass; in the hires pass (hires_steps given, new scheduling) steps count on from
+    base_steps and fractions from 1.0."""
+    if hires_steps is None or use_old_scheduling:
+        int_offset, flt_offset, steps = 0, 0.0, base_steps
+    else:
+        int_offset, flt_offset, steps = base_steps, 1.0, hires_steps
+
+    def when_step(number: str) -> int:
+        v = float(number)
+        if use_old_scheduling:
+            v = v * steps if v < 1 else v
+        elif "." in number:
+            v = (v - flt_offset) * steps
+        else:
+            v = v - int_offset
+        return min(steps, int(v))
+
+    def boundaries(node, out):
+        if isinstance(node, str) or node is None:
+            return
+        if node[0] == "seq":
+            for child in node[1]:
+                boundaries(child, out)
+        elif node[0] == "sched":
+            w = when_step(node[3])
+            if w >= 1:
+                out.add(w)
+            boundaries(node[1], out)
+            boundaries(node[2], out)
+        else:  # alt
+            out.update(range(1, steps + 1))
+            for option in node[1]:
+                boundaries(option, out)
+
+    def render(node, step, out):
+        if node is None:
+            return
+        if isinstance(node, str):
+            out.append(node)
+        elif node[0] == "seq":
+            for child in node[1]:
+                render(child, step, out)
+        elif node[0] == "sched":
+            render(node[1] if step <= when_step(node[3]) else node[2], step, out)
+        else:
+            render(node[1][(step - 1) % len(node[1])], step, out)
+
+    def schedule_of(prompt):
+        nodes = _ScheduleSyntax(prompt).parse()
+        if nodes is None:
+            return [[steps, prompt]]
+        tree = ("seq", nodes)
+        ends = {steps}
+        boundaries(tree, ends)
+        result = []
+        for t in sorted(ends):
+            out = []
+            render(tree, t, out)
+            result.append([t, "".join(out)])
+        return result
+
+    by_prompt = {prompt: schedule_of(prompt) for prompt in set(prompts)}
+    return [by_prompt[prompt] for prompt in prompts]
+
+
+class SdConditioning(list):
+    """modules/prompt_parser.py:140-152: the prompts handed to the conditioner, plus what SDXL needs to know about the job."""
+
+    def __init__(self, prompts, is_negative_prompt=False, width=None, height=None, copy_from=None):
+        super().__init__()
+        self.extend(prompts)
+        if copy_from is None:
+            copy_from = prompts
+        self.is_negative_prompt = is_negative_prompt or getattr(copy_from, "is_negative_prompt", False)
+        self.width = width or getattr(copy_from, "width", None)
+        self.height = height or getattr(copy_from, "height", None)
+
+
+def get_learned_conditioning(model, prompts, steps, hires_steps=None, use_old_scheduling=False):
+    """:155-203 — prompts -> list (per prompt) of [ScheduledPromptConditioning(end_at_step, cond), ...]; all texts of one
+    prompt's schedule are encoded in one `model.get_learned_conditioning` call, equal prompts share their schedule."""
+    res, cache = [], {}
+    for prompt, schedule in zip(prompts, get_learned_conditioning_prompt_schedules(prompts, steps, hires_steps, use_old_scheduling)):
+        if prompt in cache:
+            res.append(cache[prompt])
+            continue
+        conds = model.get_learned_conditioning(SdConditioning([text for _, text in schedule], copy_from=prompts))
+        cond_schedule = []
+        for i, (end_at_step, _) in enumerate(schedule):
+            cond = {k: v[i] for k, v in conds.items()} if isinstance(conds, dict) else conds[i]
+            cond_schedule.append(ScheduledPromptConditioning(end_at_step, cond))
+        cache[prompt] = cond_schedule
+        res.append(cond_schedule)
+    return res
+
+
+def get_multicond_learned_conditioning(model, prompts, steps, hires_steps=None, use_old_scheduling=False) -> MulticondLearnedConditioning:
+    """:246-262 — AND-split prompts -> MulticondLearnedConditioning (what `p.c` is)."""
+    per_prompt, flat, _ = get_multicond_prompt_list(prompts)
+    flat = SdConditioning(flat, copy_from=prompts)
+    learned = get_learned_conditioning(model, flat, steps, hires_steps, use_old_scheduling)
+    batch = [[ComposableScheduledPromptConditioning(learned[i], weight) for i, weight in parts] for parts in per_prompt]
+    return MulticondLearnedConditioning(shape=(len(prompts),), batch=batch)

@@ -872,6 +872,11 @@ class KDiffusionSampler:
                                                                  sigmas=sigma_sched, **extra))
 
 
+def find_sampler_config(name):
+    """modules/sd_samplers.py:18-24 — (label, function, options) of a sampler by label or alias, None when unknown."""
+    return _sampler_map.get(str(name).lower())
+
+
 def create_sampler(name, model) -> KDiffusionSampler:
     """modules/sd_samplers.py:33."""
     return KDiffusionSampler(name, model)

@@ -193,3 +193,59 @@ def test_open_clip2_pooled_and_sdxl_conditioning(cuda):
     assert float(uc["crossattn"].abs().max()) == 0.0 and float(uc["vector"][:, :320].abs().max()) == 0.0
     g.close()
     l.close()
+
+
+def test_prompt_driven_txt2img(cuda):
+    """process_images with PROMPTS: setup_conds -> prompt_parser (editing, AND, weights) -> CLIP on the engine -> CFGDenoiser
+    with per-step reconstruct_*_batch -> UNet / VAE engines. Must equal the same job fed the containers built by hand, and
+    prompt editing must actually switch the conditioning mid-sampling."""
+    from oracle.clip import CLIPTextModel, tiny_clip_config
+    from oracle.synth import init_module_
+    from oracle.unet import UNetModel, tiny_config
+    from oracle.vae import AutoencoderKLDecode, tiny_vae_config
+    from sdwebui_b200 import prompt_parser as P
+    from sdwebui_b200.engine import UNetSpec, VAEDecoderEngine, VAESpec
+    from sdwebui_b200.processing import SdModel, StableDiffusionProcessingTxt2Img, process_images
+    from sdwebui_b200.sd_hijack_clip import FrozenCLIPEmbedderWithCustomWords
+    from sdwebui_b200.sd_unet import SdxeUnet
+
+    dtype = torch.float16
+    ucfg, vcfg = tiny_config(), tiny_vae_config()
+    unet = init_module_(UNetModel(ucfg), 1).eval().to(cuda)
+    vae = init_module_(AutoencoderKLDecode(vcfg), 2).eval().to(cuda)
+    su = SdxeUnet(unet.state_dict(), UNetSpec.from_any(ucfg), dtype=dtype, device=cuda)
+    su.activate()
+    ve = VAEDecoderEngine(VAESpec.from_any(vcfg), dtype=dtype, device=cuda)
+    ve.load_state_dict(vae.state_dict())
+    ve.finalize()
+    model = SdModel(su, ve, is_sdxl=False, dtype_unet=dtype, device=cuda)
+    cfg = tiny_clip_config()
+    cfg.hidden_size, cfg.num_heads, cfg.intermediate_size = ucfg.context_dim, 2, 4 * ucfg.context_dim
+    torch.manual_seed(11)
+    clip = CLIPTextModel(cfg).eval().to(cuda)
+    with torch.no_grad():
+        clip.text_model.final_layer_norm.bias.add_(0.3)   # EmphasisOriginal divides by the chunk mean
+
+    def tok(texts, truncation=False, add_special_tokens=False):
+        return {"input_ids": [[7 if w == "," else 10 + (sum((i + 1) * ord(c) for i, c in enumerate(w)) % (cfg.vocab_size - 20)) for w in re.findall(r"[A-Za-z0-9]+|,", t)] for t in texts]}
+
+    tokenizer = type("Tok", (), {"__call__": staticmethod(tok), "get_vocab": staticmethod(lambda: {",</w>": 7}),
+                                 "bos_token_id": cfg.id_start, "eos_token_id": cfg.id_end})()
+    model.cond_stage_model = FrozenCLIPEmbedderWithCustomWords(clip.state_dict(), tokenizer, dtype=dtype, device=cuda)
+    T2I = StableDiffusionProcessingTxt2Img
+    for cache in (T2I.cached_uc, T2I.cached_c, T2I.cached_hr_uc, T2I.cached_hr_c):
+        cache[0] = cache[1] = None
+    kw = dict(sd_model=model, seeds=[5, 6], steps=6, sampler_name="Euler a", cfg_scale=6.0, width=64, height=64, randn_source="NV")
+    prompts, negatives = ["a [red:blue:0.5] (crown:1.3) AND jeweled :0.6", "a red crown"], ["blurry", ""]
+    a = process_images(T2I(prompts=prompts, negative_prompts=negatives, **kw), to_host=True)
+    # the same job with the containers built by hand
+    c = P.get_multicond_learned_conditioning(model, P.SdConditioning(prompts, width=64, height=64), 6)
+    uc = P.get_learned_conditioning(model, P.SdConditioning(negatives, is_negative_prompt=True, width=64, height=64), 6)
+    assert [s.end_at_step for s in c.batch[0][0].schedules] == [3, 6] and len(c.batch[0]) == 2 and c.batch[0][1].weight == 0.6
+    b = process_images(T2I(c=c, uc=uc, **kw), to_host=True)
+    assert torch.equal(a.images, b.images) and torch.equal(a.latents, b.latents)
+    # without the edit the first image changes (second prompt is the same in both jobs: it must not)
+    plain = process_images(T2I(prompts=["a red (crown:1.3) AND jeweled :0.6", "a red crown"], negative_prompts=negatives, **kw), to_host=True)
+    assert not torch.equal(plain.latents[0], a.latents[0]) and torch.equal(plain.latents[1], a.latents[1])
+    assert torch.isfinite(a.latents).all()
+    model.cond_stage_model.close()
