@@ -115,6 +115,14 @@ int sdxe_vae_encode(sdxe_engine* e, const void* x, void* out, int n, int h, int 
 int sdxe_clip_forward(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
                       void* stream);
 
+/* The same with textual-inversion "fixes" (modules/sd_hijack.py:340-366 EmbeddingsWithFixes.forward, fed by
+ * modules/sd_hijack_clip.py:162-176, 219): before the position embedding is added, row fix_rows[i] (= batch * T + position) of
+ * the token embedding is replaced by the learned vector fix_vecs[i, :] (engine 16-bit type, [n_fix, clip_hidden]); when a row
+ * is named more than once the last entry wins (fixes apply in order). fix_rows / fix_vecs are device pointers; n_fix = 0 is
+ * sdxe_clip_forward. */
+int sdxe_clip_forward_fixes(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
+                            const int32_t* fix_rows, const void* fix_vecs, int n_fix, void* stream);
+
 /* Cross-attention K / V cache. The context of a job does not change between sampler steps (CFGDenoiser.forward re-sends the
  * same cond_in every step, modules/sd_samplers_cfg_denoiser.py:236-249), but its k | v projections (one GEMM over all
  * transformer blocks) would be recomputed by every sdxe_unet_forward call. A non-zero `key` set before a call promises that

@@ -43,9 +43,21 @@ class _Embeddings(nn.Module):
         self.token_embedding = nn.Embedding(c.vocab_size, c.hidden_size)
         self.position_embedding = nn.Embedding(c.max_positions, c.hidden_size)
 
-    def forward(self, ids):
+    def forward(self, ids, fixes=None):
+        """`fixes`: textual-inversion replacements per batch row, [[(offset, vectors [n, C]), ...], ...] — the token embedding
+        of positions offset + 1 ... is replaced before the position embedding is added (modules/sd_hijack.py:347-366)."""
         pos = torch.arange(ids.shape[1], device=ids.device)
-        return self.token_embedding(ids) + self.position_embedding(pos)[None]
+        tok = self.token_embedding(ids)
+        if fixes:
+            rows = []
+            for row_fixes, tensor in zip(fixes, tok):
+                for offset, vec in row_fixes:
+                    vec = vec.to(tensor.device, tensor.dtype)
+                    n = min(tensor.shape[0] - offset - 1, vec.shape[0])
+                    tensor = torch.cat([tensor[0:offset + 1], vec[0:n], tensor[offset + 1 + n:]])
+                rows.append(tensor)
+            tok = torch.stack(rows)
+        return tok + self.position_embedding(pos)[None]
 
 
 class _Attention(nn.Module):
@@ -113,18 +125,18 @@ class CLIPTextModel(nn.Module):
         self.cfg = c
         self.text_model = _TextModel(c)
 
-    def hidden_states(self, ids) -> List[torch.Tensor]:
+    def hidden_states(self, ids, fixes=None) -> List[torch.Tensor]:
         """[embeddings, after layer 1, ..., after layer L] — `output_hidden_states` of the HF model."""
-        x = self.text_model.embeddings(ids)
+        x = self.text_model.embeddings(ids, fixes)
         hs = [x]
         for layer in self.text_model.encoder.layers:
             x = layer(x)
             hs.append(x)
         return hs
 
-    def encode_with_transformers(self, ids, stop_at_last_layers: int = 1):
+    def encode_with_transformers(self, ids, stop_at_last_layers: int = 1, fixes=None):
         """modules/sd_hijack_clip.py:351-360: last_hidden_state, or hidden_states[-n] through the final LayerNorm."""
-        hs = self.hidden_states(ids)
+        hs = self.hidden_states(ids, fixes)
         z = hs[-1] if stop_at_last_layers <= 1 else hs[-stop_at_last_layers]
         return self.text_model.final_layer_norm(z)
 

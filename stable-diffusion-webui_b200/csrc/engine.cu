@@ -237,6 +237,9 @@ struct Plan {
   int64_t kv_key = 0;       // context key the plan's cross-attention k|v buffer was computed under (0 = none)
   // per-call caller pointers, read by pre / post ops
   const void *x = nullptr, *t = nullptr, *ctx = nullptr, *y = nullptr;
+  const int32_t* fix_rows = nullptr;  // CLIP: textual-inversion fixes of this call (device pointers), n_fix = 0: none
+  const void* fix_vecs = nullptr;
+  int n_fix = 0;
   void* out = nullptr;
   int io_dtype = 0;
   int launches_body = 0;
@@ -1450,7 +1453,12 @@ int build_clip_plan(sdxe_engine* e, Plan* plan, int n, int T, int layer, int fin
     const int vocab = cfg.clip_vocab;
     plan->pre.push_back([=](cudaStream_t s) {
       count_launch();
-      return clip_embed_launch((const int32_t*)plan->x, tok, pos, xp, sp, (int)M, T, C, vocab, b, s);
+      ECHK(clip_embed_launch((const int32_t*)plan->x, tok, pos, xp, sp, (int)M, T, C, vocab, b, s));
+      if (plan->n_fix > 0) {
+        count_launch();
+        ECHK(clip_fix_launch(plan->fix_rows, plan->fix_vecs, pos, xp, sp, plan->n_fix, (int)M, T, C, b, s));
+      }
+      return 0;
     });
   }
   const float scale = 1.0f / sqrtf((float)d);
@@ -1711,13 +1719,20 @@ int sdxe_unet_forward(sdxe_engine* e, const void* x, const void* t, const void* 
 
 int sdxe_clip_forward(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
                       void* stream) {
+  return sdxe_clip_forward_fixes(e, tokens, out, n, T, layer, final_norm, io_dtype, nullptr, nullptr, 0, stream);
+}
+
+int sdxe_clip_forward_fixes(sdxe_engine* e, const int32_t* tokens, void* out, int n, int T, int layer, int final_norm, int io_dtype,
+                            const int32_t* fix_rows, const void* fix_vecs, int n_fix, void* stream) {
   if (!e || !e->finalized || e->cfg.kind != SDXE_MODEL_CLIP_TEXT) EFAIL("sdxe_clip_forward: engine is not a finalized CLIP text model");
   if (!tokens || !out || n <= 0 || T <= 0 || T > e->cfg.clip_positions || layer < 0 || layer > e->cfg.clip_layers) EFAIL("sdxe_clip_forward: bad argument");
   if (io_dtype != e->dt && io_dtype != SDXE_F32) EFAIL("sdxe_clip_forward: out must be the engine's 16-bit type or fp32");
   const std::string key = "c:" + std::to_string(n) + ":" + std::to_string(T) + ":" + std::to_string(layer) + ":" + std::to_string(final_norm ? 1 : 0);
   Plan* p = get_plan(e, key, [&](Plan* pl) { return build_clip_plan(e, pl, n, T, layer, final_norm ? 1 : 0); });
   if (!p) return -1;
+  if (n_fix < 0 || (n_fix > 0 && (!fix_rows || !fix_vecs))) EFAIL("sdxe_clip_forward_fixes: bad fix arguments");
   p->x = tokens; p->out = out; p->io_dtype = io_dtype;
+  p->fix_rows = fix_rows; p->fix_vecs = fix_vecs; p->n_fix = n_fix;
   return run_plan(e, p, (cudaStream_t)stream);
 }
 

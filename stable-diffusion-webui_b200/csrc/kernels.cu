@@ -858,6 +858,46 @@ int clip_embed_launch(const int32_t* ids, const void* tok, const void* pos, void
   return 0;
 }
 
+// Textual-inversion "fixes" (modules/sd_hijack.py:340-366 EmbeddingsWithFixes): row rows[i] of the token embedding is replaced by
+// the learned vector vec[i] before the position embedding is added: x[row, :] = round16(vec[i, :] + pos[row % T, :]), and
+// the row's LayerNorm partial is recomputed. One warp per fix; a row named twice takes the LAST vector (fixes apply in order).
+template <bool BF16>
+__global__ void clip_fix_kernel(const int32_t* __restrict__ rows, const typename T16<BF16>::type* __restrict__ vec,
+                                const typename T16<BF16>::type* __restrict__ pos, typename T16<BF16>::type* __restrict__ x,
+                                float2* __restrict__ stat, int n_fix, int M, int T, int C) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n_fix) return;
+  const int m = rows[i];
+  if (m < 0 || m >= M) return;
+  for (int j = i + 1; j < n_fix; ++j)
+    if (rows[j] == m) return;  // a later fix owns this row
+  const typename T16<BF16>::type* vr = vec + (size_t)i * C;
+  const typename T16<BF16>::type* pr = pos + (size_t)(m % T) * C;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const typename T16<BF16>::type v = T16<BF16>::from_f(T16<BF16>::to_f(vr[c]) + T16<BF16>::to_f(pr[c]));
+    x[(size_t)m * C + c] = v;
+    const float f = T16<BF16>::to_f(v);
+    s += f;
+    q = fmaf(f, f, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) stat[m] = make_float2(s, q);
+}
+int clip_fix_launch(const int32_t* rows, const void* vec, const void* pos, void* x, float2* stat, int n_fix, int M, int T, int C,
+                    bool bf16, cudaStream_t s) {
+  if (n_fix <= 0) return 0;
+  const int blocks = (n_fix * 32 + 255) / 256;
+  if (bf16) clip_fix_kernel<true><<<blocks, 256, 0, s>>>(rows, (const __nv_bfloat16*)vec, (const __nv_bfloat16*)pos, (__nv_bfloat16*)x, stat, n_fix, M, T, C);
+  else clip_fix_kernel<false><<<blocks, 256, 0, s>>>(rows, (const __half*)vec, (const __half*)pos, (__half*)x, stat, n_fix, M, T, C);
+  SDXE_LAUNCH_CHECK();
+  return 0;
+}
+
 // Causal self-attention over short sequences: qkv [B*T, 3C] (q | k | v, heads contiguous inside each), one CTA per
 // (batch, head), K and V of the head in shared memory, one warp per query row (token t attends to tokens <= t), fp32 math.
 template <bool BF16>

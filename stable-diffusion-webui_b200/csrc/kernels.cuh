@@ -39,6 +39,8 @@ int lincomb_launch(float* out, const float* p0, float c0, const float* p1, float
 // CLIP text encoder pieces (kernels.cu)
 int clip_embed_launch(const int32_t* ids, const void* tok, const void* pos, void* x, float2* stat, int M, int T, int C, int vocab,
                       bool bf16, cudaStream_t s);
+int clip_fix_launch(const int32_t* rows, const void* vec, const void* pos, void* x, float2* stat, int n_fix, int M, int T, int C,
+                    bool bf16, cudaStream_t s);
 int causal_attn_small_launch(const void* qkv, void* out, int B, int T, int H, int d, float scale, bool bf16, cudaStream_t s);
 int act_inplace_launch(void* x, int64_t n, int mode, bool bf16, cudaStream_t s);
 int cast_to_f32_launch(const void* src, int src_dtype, float* dst, int64_t n, bool round16, bool bf16, cudaStream_t s);

@@ -366,9 +366,11 @@ class CLIPTextEngine(_EngineBase):
         return super().load_state_dict(sd, prefix, only)
 
     def forward(self, tokens: torch.Tensor, layer: Optional[int] = None, final_norm: bool = True,
-                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+                out_dtype: Optional[torch.dtype] = None, fixes=None) -> torch.Tensor:
         """tokens [n, T] integer -> hidden_states[layer] ([n, T, C]; layer = number of transformer layers applied, default
-        all), through final_layer_norm when `final_norm`. Result in the engine's dtype (or fp32)."""
+        all), through final_layer_norm when `final_norm`. Result in the engine's dtype (or fp32).
+        `fixes`: textual-inversion replacements [(flat row = batch * T + position, vector [C]), ...] applied in order to the
+        token embedding (modules/sd_hijack.py:340-366)."""
         if tokens.dim() != 2:
             raise L.SdxeError("tokens must be [n, T]")
         n, T = tokens.shape
@@ -376,9 +378,20 @@ class CLIPTextEngine(_EngineBase):
         ids = tokens.to(device=self.device, dtype=torch.int32).contiguous()
         odt = out_dtype or self.dtype
         out = torch.empty(n, T, self.spec.hidden_size, dtype=odt, device=self.device)
+        rows = vecs = None
+        n_fix = 0
+        if fixes:
+            for r, v in fixes:
+                if not (0 <= int(r) < n * T) or v.numel() != self.spec.hidden_size:
+                    raise L.SdxeError(f"textual-inversion fix: row {r} / vector of {v.numel()} values do not fit [{n} x {T}, {self.spec.hidden_size}]")
+            rows = torch.tensor([int(r) for r, _ in fixes], dtype=torch.int32, device=self.device)
+            vecs = torch.stack([v.reshape(-1) for _, v in fixes]).to(device=self.device, dtype=self.dtype).contiguous()
+            n_fix = len(fixes)
         with torch.cuda.device(self.device):
-            L.check(self.lib.sdxe_clip_forward(self._h, L.ptr(ids), L.ptr(out), n, T, layer, 1 if final_norm else 0,
-                                               L.torch_dtype_code(odt), L.current_stream()), "sdxe_clip_forward")
+            L.check(self.lib.sdxe_clip_forward_fixes(self._h, L.ptr(ids), L.ptr(out), n, T, layer, 1 if final_norm else 0,
+                                                     L.torch_dtype_code(odt), L.ptr(rows), L.ptr(vecs), n_fix, L.current_stream()),
+                    "sdxe_clip_forward_fixes")
+        del rows, vecs
         return out
 
     __call__ = forward

@@ -12,7 +12,9 @@ running on the sdxe engine. Host mirror of modules/sd_hijack_clip.py (same class
 quick-GELU MLP, LayerNorms folded into the tcgen05 GEMMs. The tokenizer (BPE vocabulary files) is injected by the caller —
 any object with the Hugging Face tokenizer surface the reference uses (`__call__(texts, truncation=False,
 add_special_tokens=False)["input_ids"]`, `get_vocab()`, `bos_token_id`, `eos_token_id`). Textual-inversion embeddings
-("fixes", :162-176) are upstream of this mirror: a prompt that names one is encoded as plain text.
+("custom words", :162-176, 219; modules/sd_hijack.py:340-366): every wrapper owns an `embedding_db`
+(textual_inversion.EmbeddingDatabase); a prompt that names a registered embedding reserves its vectors' positions and the
+engine overwrites those rows of the token embedding (`sdxe_clip_forward_fixes`).
 """
 from __future__ import annotations
 
@@ -24,6 +26,7 @@ import torch
 from . import lib as L
 from . import prompt_parser
 from .engine import CLIPTextEngine, CLIPTextSpec
+from .textual_inversion import EmbeddingDatabase
 
 
 class PromptChunk:
@@ -32,7 +35,7 @@ class PromptChunk:
     def __init__(self):
         self.tokens: List[int] = []
         self.multipliers: List[float] = []
-        self.fixes: list = []  # textual-inversion markers in the reference; always empty here
+        self.fixes: list = []  # [(offset inside the 75 content tokens, Embedding)]: vectors go to positions offset + 1 ...
 
 
 class TextOptions:
@@ -71,6 +74,8 @@ class TextConditionalModel:
         self.id_start = None
         self.id_end = None
         self.id_pad = None
+        self.embedding_db = EmbeddingDatabase()    # the reference's model_hijack.embedding_db
+        self.textual_inversion_key = "clip_l"      # which part of an SDXL embedding this encoder takes
 
     def empty_chunk(self) -> PromptChunk:
         chunk = PromptChunk()
@@ -84,8 +89,21 @@ class TextConditionalModel:
     def tokenize(self, texts):
         raise NotImplementedError
 
-    def encode_with_transformers(self, tokens):
+    def encode_with_transformers(self, tokens, fixes=None):
         raise NotImplementedError
+
+    def fix_rows(self, batch_fixes, T: int):
+        """EmbeddingsWithFixes.forward (modules/sd_hijack.py:347-366) as a list of row replacements: for batch row b and fix
+        (offset, embedding), token positions offset + 1 ... take the embedding's vectors (as many as fit before position T),
+        in order — a later fix overwrites an earlier one. -> [(b * T + position, vector [dim]), ...]"""
+        out = []
+        for b, fixes in enumerate(batch_fixes or []):
+            for offset, embedding in fixes:
+                vec = embedding.vec[self.textual_inversion_key] if isinstance(embedding.vec, dict) else embedding.vec
+                emb_len = min(T - offset - 1, vec.shape[0])
+                for j in range(emb_len):
+                    out.append((b * T + offset + 1 + j, vec[j]))
+        return out
 
     def tokenize_line(self, line: str):
         """one prompt -> (list of PromptChunk, token count). Emphasis syntax gives per-token multipliers; the word BREAK
@@ -118,7 +136,9 @@ class TextConditionalModel:
             if text == "BREAK" and weight == -1:
                 close()
                 continue
-            for token in tokens:
+            position = 0
+            while position < len(tokens):
+                token = tokens[position]
                 if token == self.comma_token:
                     last_comma = len(cur.tokens)
                 elif backtrack != 0 and len(cur.tokens) == self.chunk_length and last_comma != -1 and len(cur.tokens) - last_comma <= backtrack:
@@ -129,8 +149,19 @@ class TextConditionalModel:
                     cur.tokens, cur.multipliers = moved_t, moved_m
                 if len(cur.tokens) == self.chunk_length:
                     close()
-                cur.tokens.append(token)
-                cur.multipliers.append(weight)
+                embedding, name_tokens = self.embedding_db.find_embedding_at_position(tokens, position)
+                if embedding is None:
+                    cur.tokens.append(token)
+                    cur.multipliers.append(weight)
+                    position += 1
+                    continue
+                emb_len = int(embedding.vectors)           # :166-176: the vectors never straddle a chunk boundary
+                if len(cur.tokens) + emb_len > self.chunk_length:
+                    close()
+                cur.fixes.append((len(cur.tokens), embedding))
+                cur.tokens += [0] * emb_len
+                cur.multipliers += [weight] * emb_len
+                position += name_tokens
         if cur.tokens or not chunks:
             close(is_last=True)
         return chunks, token_count
@@ -153,7 +184,7 @@ class TextConditionalModel:
         zs, pooled0 = [], None
         for i in range(chunk_count):
             batch_chunk = [chunks[i] if i < len(chunks) else self.empty_chunk() for chunks in batch_chunks]
-            z, pooled = self.process_tokens([x.tokens for x in batch_chunk], [x.multipliers for x in batch_chunk])
+            z, pooled = self.process_tokens([x.tokens for x in batch_chunk], [x.multipliers for x in batch_chunk], [x.fixes for x in batch_chunk])
             zs.append(z)
             if i == 0:
                 pooled0 = pooled
@@ -162,13 +193,16 @@ class TextConditionalModel:
 
     __call__ = forward
 
-    def process_tokens(self, remade_batch_tokens, batch_multipliers):
+    def process_tokens(self, remade_batch_tokens, batch_multipliers, batch_fixes=None):
         tokens = torch.asarray(remade_batch_tokens)
         if self.id_end != self.id_pad:  # SD2-style tokenizers pad with a different id than end-of-text
             for pos in range(len(remade_batch_tokens)):
                 index = remade_batch_tokens[pos].index(self.id_end)
                 tokens[pos, index + 1:tokens.shape[1]] = self.id_pad
-        z = self.encode_with_transformers(tokens)
+        if batch_fixes is not None and any(batch_fixes):
+            z = self.encode_with_transformers(tokens, batch_fixes)
+        else:
+            z = self.encode_with_transformers(tokens)
         pooled = getattr(z, "pooled", None)
         fn = EMPHASIS.get(self.opts.emphasis, _emphasis_original)
         z = fn(z, torch.asarray(batch_multipliers).to(z.device, z.dtype))
@@ -196,10 +230,15 @@ class FrozenCLIPEmbedderWithCustomWords(TextConditionalModel):
     def tokenize(self, texts):
         return self.tokenizer(texts, truncation=False, add_special_tokens=False)["input_ids"]
 
-    def encode_with_transformers(self, tokens):
+    def encode_with_transformers(self, tokens, fixes=None):
         skip = int(self.opts.CLIP_stop_at_last_layers)
         # last_hidden_state == final_layer_norm(hidden_states[-1]); clip skip n: final_layer_norm(hidden_states[-n])
-        return self.engine.forward(tokens, layer=self.spec.num_layers - (skip - 1 if skip > 1 else 0), final_norm=True)
+        return self.engine.forward(tokens, layer=self.spec.num_layers - (skip - 1 if skip > 1 else 0), final_norm=True,
+                                   fixes=self.fix_rows(fixes, tokens.shape[1]))
+
+    def load_embedding(self, path: str):
+        """registers the embedding file under its base name if its width fits this encoder (textual_inversion.py:157-203)."""
+        return self.embedding_db.load_from_file(path, self.tokenize, expected_shape=self.spec.hidden_size)
 
     def close(self):
         self.engine.close()
@@ -212,15 +251,16 @@ class FrozenCLIPEmbedderForSDXLWithCustomWords(FrozenCLIPEmbedderWithCustomWords
         super().__init__(*args, **kwargs)
         self.layer, self.layer_idx = layer, layer_idx
 
-    def encode_with_transformers(self, tokens):
+    def encode_with_transformers(self, tokens, fixes=None):
         n = self.spec.num_layers
+        rows = self.fix_rows(fixes, tokens.shape[1])
         if self.opts.sdxl_clip_l_skip is True:
             idx = n + 1 - int(self.opts.CLIP_stop_at_last_layers)   # hidden_states[-skip] of n + 1 states
-            return self.engine.forward(tokens, layer=idx, final_norm=False)
+            return self.engine.forward(tokens, layer=idx, final_norm=False, fixes=rows)
         if self.layer == "last":
-            return self.engine.forward(tokens, layer=n, final_norm=True)
+            return self.engine.forward(tokens, layer=n, final_norm=True, fixes=rows)
         idx = self.layer_idx if self.layer_idx >= 0 else n + 1 + self.layer_idx
-        return self.engine.forward(tokens, layer=idx, final_norm=False)
+        return self.engine.forward(tokens, layer=idx, final_norm=False, fixes=rows)
 
 
 def open_clip_to_hf_state_dict(sd, prefix: str = "model."):
@@ -275,16 +315,18 @@ class FrozenOpenCLIPEmbedder2WithCustomWords(TextConditionalModel):
         self.id_start = tokenizer.encoder["<start_of_text>"]
         self.id_end = tokenizer.encoder["<end_of_text>"]
         self.id_pad = 0
+        self.textual_inversion_key = "clip_g"      # modules/sd_hijack.py:62 wraps this tower's token embedding with 'clip_g'
 
     def tokenize(self, texts):
         return [self.tokenizer.encode(text) for text in texts]
 
-    def encode_with_transformers(self, tokens):
+    def encode_with_transformers(self, tokens, fixes=None):
         from . import ops
 
         n = self.spec.num_layers
-        z = self.engine.forward(tokens, layer=n - 1 if self.layer == "penultimate" else n, final_norm=self.layer != "penultimate")
-        last = z if self.layer != "penultimate" else self.engine.forward(tokens, layer=n, final_norm=True)
+        rows_fix = self.fix_rows(fixes, tokens.shape[1])
+        z = self.engine.forward(tokens, layer=n - 1 if self.layer == "penultimate" else n, final_norm=self.layer != "penultimate", fixes=rows_fix)
+        last = z if self.layer != "penultimate" else self.engine.forward(tokens, layer=n, final_norm=True, fixes=rows_fix)
         eot = tokens.to(last.device).argmax(dim=-1)                      # open_clip pools at the highest token id = <end_of_text>
         rows = last[torch.arange(last.shape[0], device=last.device), eot].contiguous()
         pooled = ops.gemm(rows, self.text_projection_t)                  # tcgen05 GEMM, M = number of prompts

@@ -249,3 +249,73 @@ def test_prompt_driven_txt2img(cuda):
     assert not torch.equal(plain.latents[0], a.latents[0]) and torch.equal(plain.latents[1], a.latents[1])
     assert torch.isfinite(a.latents).all()
     model.cond_stage_model.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_textual_inversion_fixes(cuda, dtype):
+    """sdxe_clip_forward_fixes vs the oracle (pinned to transformers.CLIPTextModel with its token embedding wrapped as the
+    reference wraps it, tests/test_clip_oracle_cpu.py): rows replaced before the position embedding, last fix wins, a fix that
+    runs past the sequence is cut; then the prompt path: a registered embedding changes exactly the prompts that name it."""
+    import types
+
+    from oracle.clip import CLIPTextConfig, tiny_clip_config
+    from sdwebui_b200.sd_hijack_clip import FrozenCLIPEmbedderWithCustomWords
+    from sdwebui_b200.textual_inversion import Embedding
+
+    cfg = tiny_clip_config()
+    cfg.hidden_size, cfg.num_heads, cfg.intermediate_size = 128, 2, 512
+    m, eng = _models(cuda, cfg, dtype)
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, cfg.vocab_size - 2, (3, 77), generator=g)
+    ids[:, 0] = cfg.id_start
+    vec_a, vec_b, vec_c = (torch.randn(k, cfg.hidden_size, generator=g) for k in (3, 2, 5))
+    per_row = [[(4, vec_a)], [], [(0, vec_b), (1, vec_a), (74, vec_c)]]      # (1, vec_a) overwrites part of (0, vec_b); vec_c is cut
+    flat = []
+    for b, fixes in enumerate(per_row):
+        for off, v in fixes:
+            for j in range(min(77 - off - 1, v.shape[0])):
+                flat.append((b * 77 + off + 1 + j, v[j]))
+    # the oracle sees the vectors as the engine stores them (16-bit)
+    per_row16 = [[(off, v.to(dtype).float()) for off, v in fixes] for fixes in per_row]
+    with torch.no_grad():
+        hs = m.hidden_states(ids.to(cuda), per_row16)
+        plain = m.hidden_states(ids.to(cuda))
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    for layer in (1, cfg.num_layers):
+        got = eng.forward(ids, layer=layer, final_norm=False, fixes=flat)
+        e = rel_err(got, hs[layer])
+        print(f"TI fixes {dtype} layer {layer}: rel err {e:.3e} (without the fixes {rel_err(got, plain[layer]):.3e})")
+        assert e < tol and rel_err(got, plain[layer]) > 10 * tol
+    assert torch.equal(eng.forward(ids, layer=2, final_norm=True), eng.forward(ids, layer=2, final_norm=True, fixes=[]))
+    eng.close()
+    if dtype != torch.float16:
+        return
+
+    def tok(texts, truncation=False, add_special_tokens=False):
+        return {"input_ids": [[7 if w == "," else 10 + (sum((i + 1) * ord(c) for i, c in enumerate(w)) % (cfg.vocab_size - 20)) for w in re.findall(r"[A-Za-z0-9]+|,", t)] for t in texts]}
+
+    tokenizer = type("Tok", (), {"__call__": staticmethod(tok), "get_vocab": staticmethod(lambda: {",</w>": 7}),
+                                 "bos_token_id": cfg.id_start, "eos_token_id": cfg.id_end})()
+    with torch.no_grad():
+        m.text_model.final_layer_norm.bias.add_(0.3)
+    emb = FrozenCLIPEmbedderWithCustomWords(m.state_dict(), tokenizer, dtype=dtype, device=cuda)
+    before = emb.forward(["a photo of wizardstyle", "a photo of a cat"])
+    e = Embedding(vec_a, "wizardstyle")
+    e.vectors, e.shape = 3, cfg.hidden_size
+    emb.embedding_db.register_embedding(e, emb.tokenize)
+    after = emb.forward(["a photo of wizardstyle", "a photo of a cat"])
+    assert torch.equal(before[1], after[1]) and not torch.allclose(before[0], after[0], atol=1e-2)
+    chunks, count = emb.tokenize_line("a photo of wizardstyle")
+    assert count == 6 and chunks[0].fixes[0][0] == 3 and chunks[0].tokens[4:7] == [0, 0, 0]
+    with torch.no_grad():
+        ids1 = torch.tensor([chunks[0].tokens], device=cuda)
+        want = m.encode_with_transformers(ids1, 1, [[(3, vec_a.to(dtype).float())]])
+        unfixed = m.encode_with_transformers(ids1, 1)
+    mult = torch.tensor([chunks[0].multipliers], device=cuda)
+    from oracle.clip import emphasis_original
+
+    # (the widened test weights put ~7e-3 of fp16 error through the final LayerNorm; the unfixed encoding is 50x further away)
+    e_fix, e_plain = rel_err(after[0:1], emphasis_original(want, mult)), rel_err(after[0:1], emphasis_original(unfixed, mult))
+    print(f"prompt with embedding -> cond: rel err {e_fix:.3e} (against the encoding without the embedding {e_plain:.3e})")
+    assert e_fix < 1.2e-2 and e_plain > 20 * e_fix
+    emb.close()

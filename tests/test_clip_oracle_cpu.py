@@ -43,6 +43,44 @@ def test_matches_transformers_clip_text_model(cfg):
         assert torch.allclose(mine.encode_with_transformers(ids, 2), want, atol=2e-5, rtol=1e-5)
 
 
+def test_textual_inversion_fixes_match_wrapped_token_embedding():
+    """The reference applies embeddings by wrapping the HF model's token_embedding (modules/sd_hijack.py:340-366, installed at
+    :196-231). Same wrapping here around transformers.CLIPTextModel vs the oracle's `fixes` argument."""
+    cfg = tiny_clip_config()
+    torch.manual_seed(3)
+    hf = _hf(cfg)
+    mine = CLIPTextModel(cfg).eval()
+    mine.load_state_dict({k: v for k, v in hf.state_dict().items() if "position_ids" not in k}, strict=False)
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, cfg.vocab_size - 2, (3, 77), generator=g)
+    ids[:, 0] = cfg.id_start
+    fixes = [[(4, torch.randn(3, cfg.hidden_size, generator=g))], [],
+             [(0, torch.randn(2, cfg.hidden_size, generator=g)), (74, torch.randn(5, cfg.hidden_size, generator=g))]]  # the last one is cut at position 77
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, input_ids):
+            e = self.inner(input_ids)
+            rows = []
+            for row_fixes, tensor in zip(fixes, e):
+                for offset, vec in row_fixes:
+                    n = min(tensor.shape[0] - offset - 1, vec.shape[0])
+                    tensor = torch.cat([tensor[0:offset + 1], vec[0:n], tensor[offset + 1 + n:]])
+                rows.append(tensor)
+            return torch.stack(rows)
+
+    hf.text_model.embeddings.token_embedding = Wrapped(hf.text_model.embeddings.token_embedding)
+    with torch.no_grad():
+        out = hf(input_ids=ids, output_hidden_states=True)
+        hs = mine.hidden_states(ids, fixes)
+        for a, b in zip(hs, out.hidden_states):
+            assert torch.allclose(a, b, atol=2e-5, rtol=1e-5), (a - b).abs().max()
+        assert not torch.allclose(hs[-1], mine.hidden_states(ids)[-1], atol=1e-3)   # the fixes matter
+
+
 def test_chunks_and_emphasis():
     cfg = tiny_clip_config()
     ch = chunk_tokens([], [], cfg)
