@@ -426,7 +426,9 @@ def measure_workload(key, dtype_name, rank, world, local, device, steps, warmup,
             achieved = mm_fl / (mm_ms / 1000.0) / 1e12 if mm_ms > 0 else 0.0
             total_u = sum(v["ms"] for v in prof_u.values())
             traffic, traffic_src = None, None
-            tpath = os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")   # final-tree capture; the round-1 one is the fallback
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")
             if key == "sd15" and os.path.exists(tpath):  # ncu capture of the same kernel on the same UNet call (SD1.5, 2B = 16)
                 with open(tpath) as f:
                     tj = json.load(f)
